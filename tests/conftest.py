@@ -1,0 +1,29 @@
+import os
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), '..'))
+if ROOT not in sys.path:
+  sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.dirname(__file__))
+
+
+def pytest_configure(config):
+  config.addinivalue_line('markers', 'gpu: needs a CUDA device (B200); run with -m gpu on the GPU box')
+
+
+def pytest_collection_modifyitems(config, items):
+  if torch.cuda.is_available():
+    return
+  skip = pytest.mark.skip(reason='no CUDA device')
+  for item in items:
+    if 'gpu' in item.keywords:
+      item.add_marker(skip)
+
+
+@pytest.fixture(scope='session')
+def golden():
+  path = os.path.join(ROOT, 'tests', 'golden', 'golden_v1.pt')
+  return torch.load(path, map_location='cpu', weights_only=False)
