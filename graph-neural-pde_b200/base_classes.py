@@ -1,0 +1,207 @@
+"""ODEFunc / ODEblock / BaseGNN with the reference's constructor signatures, attribute names and state_dict keys
+(reference src/base_classes.py:32-146), rebuilt around the CUDA engine.
+
+Differences a caller can observe: none on the API; the classes are plain nn.Modules (the reference subclasses PyG's
+MessagePassing but never calls propagate) and `ODEFunc` owns a lazily built device `GraphPlan` that is
+invalidated whenever `edge_index` is reassigned from outside (reference src/run_GNN.py:252-254 does that).
+"""
+import torch
+from torch import nn
+
+from .engine import RhsEngine
+from .graph_plan import GraphPlan
+from .utils import Meter
+
+
+class RegularizedODEfunc(nn.Module):
+  """Holder that keeps `ODEblock.reg_odefunc.odefunc` (and its parameters / state_dict keys) alive
+  (reference src/regularized_ODE_function.py:8-33).  The RNODE regularisers themselves are out of the hot path's
+  scope (all coefficients default to None, reference src/run_GNN.py:370-374)."""
+
+  def __init__(self, odefunc, regularization_fns):
+    super().__init__()
+    self.odefunc = odefunc
+    self.regularization_fns = regularization_fns
+
+  def before_odeint(self, *args, **kwargs):
+    return self.odefunc.before_odeint(*args, **kwargs) if hasattr(self.odefunc, 'before_odeint') else None
+
+  def forward(self, t, state):
+    if len(self.regularization_fns) > 0:
+      raise NotImplementedError('RNODE regularisers are outside the grand_b200 hot path')
+    return self.odefunc(t, state)
+
+  @property
+  def _num_evals(self):
+    return self.odefunc._num_evals
+
+
+REGULARIZATION_KEYS = ('kinetic_energy', 'jacobian_norm2', 'total_deriv', 'directional_penalty')
+
+
+def create_regularization_fns(args):
+  """reference src/base_classes.py:18-29; any non-None coefficient is refused loudly (out of scope)."""
+  fns, coeffs = [], []
+  for key in REGULARIZATION_KEYS:
+    if args.get(key) is not None:
+      raise NotImplementedError('regulariser %r is outside the grand_b200 hot path' % key)
+  return fns, coeffs
+
+
+class ODEFunc(nn.Module):
+  """reference src/base_classes.py:77-95.  Mutable attributes assigned from outside: edge_index, edge_weight,
+  attention_weights, x0, nfe."""
+
+  def __init__(self, opt, data, device):
+    super(ODEFunc, self).__init__()
+    self.opt = opt
+    self.device = device
+    self._edge_index = None
+    self._engine = None
+    self.edge_weight = None
+    self.attention_weights = None
+    self.alpha_train = nn.Parameter(torch.tensor(0.0))
+    self.beta_train = nn.Parameter(torch.tensor(0.0))
+    self.x0 = None
+    self.nfe = 0
+    self.alpha_sc = nn.Parameter(torch.ones(1))
+    self.beta_sc = nn.Parameter(torch.ones(1))
+
+  # edge_index is a plain attribute in the reference; here assigning it drops the cached CSR plan
+  @property
+  def edge_index(self):
+    return self._edge_index
+
+  @edge_index.setter
+  def edge_index(self, value):
+    self._edge_index = value
+    self._engine = None
+
+  def engine(self, x):
+    """The CUDA engine for the current graph and state width (built on first use)."""
+    d = int(x.shape[1])
+    if self._engine is None or self._engine.d != d or self._engine.device != x.device:
+      plan = GraphPlan(self._edge_index, num_nodes=x.shape[0], device=x.device)
+      self._engine = RhsEngine(plan, d)
+    return self._engine
+
+  def _bump_nfe(self, count=1):
+    """`if self.nfe > max_nfe: raise` BEFORE the increment, once per evaluation
+    (reference src/function_transformer_attention.py:39-42)."""
+    from .utils import MaxNFEException
+    for _ in range(count):
+      if self.nfe > self.opt['max_nfe']:
+        raise MaxNFEException
+      self.nfe += 1
+
+  def __repr__(self):
+    return self.__class__.__name__
+
+
+class ODEblock(nn.Module):
+  """reference src/base_classes.py:32-74."""
+
+  def __init__(self, odefunc, regularization_fns, opt, data, device, t):
+    super(ODEblock, self).__init__()
+    self.opt = opt
+    self.t = t
+    self.device = device
+    self.aug_dim = 2 if opt['augment'] else 1
+    self.odefunc = odefunc(self.aug_dim * opt['hidden_dim'], self.aug_dim * opt['hidden_dim'], opt, data, device)
+    self.nreg = len(regularization_fns)
+    self.reg_odefunc = RegularizedODEfunc(self.odefunc, regularization_fns)
+    from .odeint import odeint, odeint_adjoint
+    self.train_integrator = odeint_adjoint if opt['adjoint'] else odeint
+    self.test_integrator = None
+    self.set_tol()
+
+  def set_x0(self, x0):
+    self.odefunc.x0 = x0.clone().detach()
+    self.reg_odefunc.odefunc.x0 = x0.clone().detach()
+
+  def set_tol(self):
+    self.atol = self.opt['tol_scale'] * 1e-7
+    self.rtol = self.opt['tol_scale'] * 1e-9
+    if self.opt['adjoint']:
+      self.atol_adjoint = self.opt['tol_scale_adjoint'] * 1e-7
+      self.rtol_adjoint = self.opt['tol_scale_adjoint'] * 1e-9
+
+  def reset_tol(self):
+    self.atol = 1e-7
+    self.rtol = 1e-9
+    self.atol_adjoint = 1e-7
+    self.rtol_adjoint = 1e-9
+
+  def set_time(self, time):
+    self.t = torch.tensor([0, time]).to(self.device)
+
+  def _integrate(self, x, integrator_options, adjoint_options):
+    """Shared tail of ConstantODEblock.forward / AttODEblock.forward
+    (reference src/block_constant.py:35-70, src/block_transformer_attention.py:36-72)."""
+    t = self.t.type_as(x)
+    integrator = self.train_integrator if self.training else self.test_integrator
+    if self.training and self.nreg > 0:
+      raise NotImplementedError('RNODE regularisers are outside the grand_b200 hot path')
+    func, state = self.odefunc, x
+    if self.opt["adjoint"] and self.training:
+      state_dt = integrator(func, state, t, method=self.opt['method'], options=integrator_options,
+                            adjoint_method=self.opt['adjoint_method'], adjoint_options=adjoint_options,
+                            atol=self.atol, rtol=self.rtol, adjoint_atol=self.atol_adjoint,
+                            adjoint_rtol=self.rtol_adjoint)
+    else:
+      state_dt = integrator(func, state, t, method=self.opt['method'], options=integrator_options, atol=self.atol,
+                            rtol=self.rtol)
+    return state_dt[1]
+
+  def __repr__(self):
+    return self.__class__.__name__ + '( Time Interval ' + str(self.t[0].item()) + ' -> ' + str(self.t[1].item()) \
+           + ")"
+
+
+class BaseGNN(nn.Module):
+  """Encoder / decoder shell, reference src/base_classes.py:98-146 (state_dict keys m1, m2, mx, mp, ... kept)."""
+
+  def __init__(self, opt, dataset, device=torch.device('cpu')):
+    super(BaseGNN, self).__init__()
+    self.opt = opt
+    self.T = opt['time']
+    self.num_classes = dataset.num_classes
+    self.num_features = dataset.data.num_features
+    self.num_nodes = dataset.data.num_nodes
+    self.device = device
+    self.fm = Meter()
+    self.bm = Meter()
+    if opt['beltrami']:
+      self.mx = nn.Linear(self.num_features, opt['feat_hidden_dim'])
+      self.mp = nn.Linear(opt['pos_enc_dim'], opt['pos_enc_hidden_dim'])
+      opt['hidden_dim'] = opt['feat_hidden_dim'] + opt['pos_enc_hidden_dim']
+    else:
+      self.m1 = nn.Linear(self.num_features, opt['hidden_dim'])
+    if self.opt['use_mlp']:
+      self.m11 = nn.Linear(opt['hidden_dim'], opt['hidden_dim'])
+      self.m12 = nn.Linear(opt['hidden_dim'], opt['hidden_dim'])
+    if opt['use_labels']:
+      opt['hidden_dim'] = opt['hidden_dim'] + dataset.num_classes
+    else:
+      self.hidden_dim = opt['hidden_dim']
+    if opt['fc_out']:
+      self.fc = nn.Linear(opt['hidden_dim'], opt['hidden_dim'])
+    self.m2 = nn.Linear(opt['hidden_dim'], dataset.num_classes)
+    if self.opt['batch_norm']:
+      self.bn_in = torch.nn.BatchNorm1d(opt['hidden_dim'])
+      self.bn_out = torch.nn.BatchNorm1d(opt['hidden_dim'])
+    self.regularization_fns, self.regularization_coeffs = create_regularization_fns(self.opt)
+
+  def getNFE(self):
+    return self.odeblock.odefunc.nfe + self.odeblock.reg_odefunc.odefunc.nfe
+
+  def resetNFE(self):
+    self.odeblock.odefunc.nfe = 0
+    self.odeblock.reg_odefunc.odefunc.nfe = 0
+
+  def reset(self):
+    self.m1.reset_parameters()
+    self.m2.reset_parameters()
+
+  def __repr__(self):
+    return self.__class__.__name__

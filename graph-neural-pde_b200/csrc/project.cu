@@ -1,0 +1,141 @@
+// Q/K projection:  Q = X Wq^T + bq (rows < n_rows),  K = X Wk^T + bk (rows < n_cols).
+// Replaces the two nn.Linear calls of reference src/function_transformer_attention.py:174-175.
+//
+// HBM-bound (reads X once, writes 2*ad floats per row); the contraction depth is d <= a few hundred, so this is a
+// register-tiled fp32 FFMA kernel: the whole [2 ad, d] weight lives in shared memory for the lifetime of a
+// persistent CTA, X row tiles stream through shared memory, every thread owns an RT x OT output block.
+// fp32 FFMA on purpose: the parity bar is 1e-5 of the reference's fp32 GEMM, which a single TF32 pass cannot meet.
+#include "common.cuh"
+
+namespace grand {
+
+constexpr int kProjThreads = 256;
+
+template <int RT, int OT>
+__global__ void __launch_bounds__(kProjThreads, 2)
+project_qk_kernel(const float* __restrict__ x, int n_rows, int n_cols, int d, int d4, int ld,
+                  const float* __restrict__ wq, const float* __restrict__ bq, const float* __restrict__ wk,
+                  const float* __restrict__ bk, int ad, int tx_count, int rows_per_tile, int n_tiles,
+                  float* __restrict__ q, float* __restrict__ k) {
+  extern __shared__ __align__(16) float smem[];
+  const int out = 2 * ad;
+  float* ws = smem;                       // [out][ld]
+  float* xs = smem + (size_t)out * ld;    // [rows_per_tile][ld]
+  const int tid = threadIdx.x;
+  const int c4n = d4 >> 2;
+
+  // stage the weights once per CTA (zero padded to d4)
+  for (int idx = tid; idx < out * d4; idx += kProjThreads) {
+    const int o = idx / d4, c = idx - o * d4;
+    float v = 0.f;
+    if (c < d) v = (o < ad) ? wq[(size_t)o * d + c] : wk[(size_t)(o - ad) * d + c];
+    ws[o * ld + c] = v;
+  }
+
+  const int tx = tid % tx_count;
+  const int ty = tid / tx_count;
+  const int ty_count = rows_per_tile / RT;
+  const bool active = ty < ty_count;
+  const bool vec_ok = (d & 3) == 0;
+
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int row0 = tile * rows_per_tile;
+    __syncthreads();  // previous tile's compute is done (and the weights are visible on the first pass)
+    if (vec_ok) {
+      for (int idx = tid; idx < rows_per_tile * c4n; idx += kProjThreads) {
+        const int r = idx / c4n, c4 = idx - r * c4n;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (row0 + r < n_cols) v = ld_stream4(x + (size_t)(row0 + r) * d + 4 * c4);
+        *reinterpret_cast<float4*>(xs + r * ld + 4 * c4) = v;
+      }
+    } else {
+      for (int idx = tid; idx < rows_per_tile * d4; idx += kProjThreads) {
+        const int r = idx / d4, c = idx - r * d4;
+        float v = 0.f;
+        if (row0 + r < n_cols && c < d) v = x[(size_t)(row0 + r) * d + c];
+        xs[r * ld + c] = v;
+      }
+    }
+    __syncthreads();
+    if (!active) continue;
+
+    float acc[RT][OT];
+#pragma unroll
+    for (int ri = 0; ri < RT; ++ri)
+#pragma unroll
+      for (int oi = 0; oi < OT; ++oi) acc[ri][oi] = 0.f;
+
+    const float* xrow = xs + (ty * RT) * ld;
+    for (int c = 0; c < d4; c += 4) {
+      float4 xv[RT], wv[OT];
+#pragma unroll
+      for (int ri = 0; ri < RT; ++ri) xv[ri] = *reinterpret_cast<const float4*>(xrow + ri * ld + c);
+#pragma unroll
+      for (int oi = 0; oi < OT; ++oi) {
+        const int o = tx + oi * tx_count;
+        wv[oi] = (o < out) ? *reinterpret_cast<const float4*>(ws + o * ld + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int ri = 0; ri < RT; ++ri)
+#pragma unroll
+        for (int oi = 0; oi < OT; ++oi) {
+          acc[ri][oi] = fmaf(xv[ri].x, wv[oi].x, acc[ri][oi]);
+          acc[ri][oi] = fmaf(xv[ri].y, wv[oi].y, acc[ri][oi]);
+          acc[ri][oi] = fmaf(xv[ri].z, wv[oi].z, acc[ri][oi]);
+          acc[ri][oi] = fmaf(xv[ri].w, wv[oi].w, acc[ri][oi]);
+        }
+    }
+#pragma unroll
+    for (int oi = 0; oi < OT; ++oi) {
+      const int o = tx + oi * tx_count;
+      if (o >= out) continue;
+      const bool is_q = o < ad;
+      const float bias = is_q ? bq[o] : bk[o - ad];
+#pragma unroll
+      for (int ri = 0; ri < RT; ++ri) {
+        const int r = row0 + ty * RT + ri;
+        const float v = acc[ri][oi] + bias;
+        if (is_q) {
+          if (r < n_rows) q[(size_t)r * ad + o] = v;
+        } else {
+          if (r < n_cols) k[(size_t)r * ad + (o - ad)] = v;
+        }
+      }
+    }
+  }
+}
+
+int launch_project_qk(const float* x, int n_rows, int n_cols, int d, const float* wq, const float* bq,
+                      const float* wk, const float* bk, int ad, float* q, float* k, cudaStream_t stream) {
+  if (n_cols <= 0) return GRAND_OK;
+  constexpr int RT = 4, OT = 4;
+  const int out = 2 * ad;
+  const int tx_count = (out + OT - 1) / OT;
+  GRAND_REQUIRE(tx_count <= kProjThreads, GRAND_EUNSUPPORTED, "project_qk: attention_dim %d too wide (max %d)", ad,
+                kProjThreads * OT / 2);
+  const int d4 = (d + 3) & ~3;
+  const int ld = ((d4 >> 2) & 1) ? d4 : d4 + 4;  // ld/4 odd -> conflict-free 128-bit shared loads across rows
+  const int ty_count = kProjThreads / tx_count;
+  const int rows_per_tile = ty_count * RT;
+  const int n_tiles = (n_cols + rows_per_tile - 1) / rows_per_tile;
+  const size_t smem = (size_t)(out + rows_per_tile) * ld * sizeof(float);
+  GRAND_REQUIRE(smem <= 227 * 1024, GRAND_EUNSUPPORTED,
+                "project_qk: [2*%d, %d] weights + row tile need %zu B of shared memory (> 227 KiB)", ad, d, smem);
+  auto kern = project_qk_kernel<RT, OT>;
+  static size_t configured = 0;
+  if (smem > configured) {
+    GRAND_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  int per_sm = (int)((227 * 1024) / (smem + 1024));
+  if (per_sm < 1) per_sm = 1;
+  if (per_sm > 4) per_sm = 4;
+  int grid = num_sms() * per_sm;
+  if (grid > n_tiles) grid = n_tiles;
+  kern<<<grid, kProjThreads, smem, stream>>>(x, n_rows, n_cols, d, d4, ld, wq, bq, wk, bk, ad, tx_count,
+                                             rows_per_tile, n_tiles, q, k);
+  GRAND_CUDA_OK(cudaGetLastError());
+  return GRAND_OK;
+}
+
+}  // namespace grand

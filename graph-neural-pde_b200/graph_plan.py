@@ -1,0 +1,92 @@
+"""Graph plan: the caller's COO `edge_index` re-laid out once for the kernels (include/grand_b200.h `grand_graph`).
+
+  * CSR by edge_index[0] -- the row torch_sparse.spmm sums into == the query node of the attention
+    (reference src/function_transformer_attention.py:190-191); a STABLE sort, so edges of a row
+    keep the caller's relative order and `eid` maps every CSR position back to the caller's edge position
+    (PyG appends self loops at the end of the list, so the caller's order is not sorted).
+  * row tiles of <= GRAND_TILE edges, one warp each; the tiles of rows that need several come first (their index
+    is their partial-sum slot), then one tile per remaining row in row order.  Every row has at least one tile,
+    also rows without edges (their output is -alpha x + beta x0).
+  * CSC view (colptr, csc_pos) for attention_norm_idx = 1.
+
+Pure index plumbing in torch ops; works on CPU tensors too (host-logic tests), the kernels only ever see the
+device copy.
+"""
+import torch
+
+from . import _native as N
+
+
+class GraphPlan:
+  def __init__(self, edge_index, num_nodes, device=None, num_cols=None, tile=N.GRAND_TILE):
+    assert edge_index.dim() == 2 and edge_index.shape[0] == 2, 'edge_index must be [2, E]'
+    device = torch.device(device) if device is not None else edge_index.device
+    ei = edge_index.to(device=device, dtype=torch.long)
+    n_rows = int(num_nodes)
+    n_cols = int(num_cols) if num_cols is not None else n_rows
+    e = ei.shape[1]
+    if e > 0:
+      assert int(ei[0].max()) < n_rows and int(ei[1].max()) < n_cols and int(ei.min()) >= 0, 'edge_index out of range'
+    assert e < 2 ** 31 and n_cols < 2 ** 31
+    row, col = ei[0], ei[1]
+    perm = torch.argsort(row, stable=True)
+    deg = torch.bincount(row, minlength=n_rows)
+    rowptr = torch.zeros(n_rows + 1, dtype=torch.long, device=device)
+    rowptr[1:] = torch.cumsum(deg, 0)
+
+    n_tiles_of_row = torch.clamp((deg + tile - 1) // tile, min=1)
+    split_rows = torch.nonzero(n_tiles_of_row > 1).flatten()
+    # longest rows first: their tiles are scheduled first and hide the tail
+    if split_rows.numel() > 0:
+      order = torch.argsort(deg[split_rows], descending=True, stable=True)
+      split_rows = split_rows[order]
+    nt_split = n_tiles_of_row[split_rows]
+    split_tile0 = torch.zeros(split_rows.numel() + 1, dtype=torch.long, device=device)
+    split_tile0[1:] = torch.cumsum(nt_split, 0)
+    n_split_tiles = int(split_tile0[-1])
+    split_index = torch.arange(split_rows.numel(), device=device)
+    st_split = torch.repeat_interleave(split_index, nt_split)                 # split-row index of each split tile
+    st_k = torch.arange(n_split_tiles, device=device) - split_tile0[:-1][st_split]
+    st_row = split_rows[st_split]
+    st_beg = rowptr[st_row] + st_k * tile
+    single_rows = torch.nonzero(n_tiles_of_row == 1).flatten()
+    tile_row = torch.cat([st_row, single_rows])
+    tile_beg = torch.cat([st_beg, rowptr[single_rows]])
+    tile_split = torch.cat([st_split, torch.full_like(single_rows, -1)])
+
+    col_csr = col[perm]
+    perm_c = torch.argsort(col_csr, stable=True)
+    cdeg = torch.bincount(col, minlength=n_cols)
+    colptr = torch.zeros(n_cols + 1, dtype=torch.long, device=device)
+    colptr[1:] = torch.cumsum(cdeg, 0)
+
+    i32 = lambda t: t.to(torch.int32).contiguous()
+    self.device = device
+    self.n_rows, self.n_cols, self.n_edges = n_rows, n_cols, e
+    self.n_tiles = int(tile_row.numel())
+    self.n_split_rows = int(split_rows.numel())
+    self.n_split_tiles = n_split_tiles
+    self.max_degree = int(deg.max()) if n_rows > 0 and e > 0 else 0
+    self.rowptr, self.col, self.erow, self.eid = i32(rowptr), i32(col_csr), i32(row[perm]), i32(perm)
+    self.tile_row, self.tile_beg, self.tile_split = i32(tile_row), i32(tile_beg), i32(tile_split)
+    self.split_tile0 = i32(split_tile0)
+    self.colptr, self.csc_pos = i32(colptr), i32(perm_c)
+    self.eid_long = perm  # CSR position -> caller position (int64, for torch-side permutations)
+    self._struct = None
+
+  def struct(self):
+    """ctypes `grand_graph` pointing at this plan's device arrays (the plan must outlive every use)."""
+    if self._struct is None:
+      g = N.GrandGraph()
+      g.n_rows, g.n_cols, g.n_edges, g.n_tiles = self.n_rows, self.n_cols, self.n_edges, self.n_tiles
+      g.n_split_rows, g.n_split_tiles = self.n_split_rows, self.n_split_tiles
+      for name in ('rowptr', 'col', 'erow', 'eid', 'tile_row', 'tile_beg', 'tile_split', 'split_tile0', 'colptr',
+                   'csc_pos'):
+        setattr(g, name, getattr(self, name).data_ptr())
+      self._struct = g
+    return self._struct
+
+  def to_csr_order(self, per_edge):
+    """Per-edge values in the caller's order -> CSR order (torch-side; the device kernel is
+    grand_edge_values_to_csr)."""
+    return per_edge[self.eid_long].contiguous()

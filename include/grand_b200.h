@@ -1,0 +1,189 @@
+/*
+ * grand_b200.h -- C ABI of the B200-native GRAND / BLEND ODE right-hand-side engine.
+ *
+ * The reference (twitter-research/graph-neural-pde) is pure Python and has no FFI of its own; its "operator API"
+ * for this path is the Python class contract `ODEFunc.forward(t, x)` / `ODEblock.forward(x)` selected by
+ * `set_function` / `set_block` (reference src/model_configurations.py:17-44).  This header is the boundary a
+ * maintainer binds UNDER that contract (ctypes stub in INTEGRATION.md): plain C, raw device pointers and sizes,
+ * one cudaStream_t (passed as void*), no torch types.
+ *
+ * Rules common to every entry point
+ *   - returns 0 on success, a negative GRAND_E* code otherwise; `grand_last_error()` has the message;
+ *   - never allocates, never synchronises, keeps no global state: every buffer (inputs, outputs, workspace) is
+ *     caller-owned device memory, so every call is CUDA-Graph capturable on `stream`;
+ *   - all floating-point data is fp32 row-major, all indices int32; sm_100a only.
+ *
+ * Each entry point cites the reference code it replaces (paths relative to the reference root).
+ */
+#ifndef GRAND_B200_H_
+#define GRAND_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GRAND_ABI_VERSION 1
+
+/* error codes */
+#define GRAND_OK 0
+#define GRAND_EINVAL (-1)      /* bad argument (null pointer, negative size, unknown enum)            */
+#define GRAND_EUNSUPPORTED (-2)/* shape outside what the kernels are built for (see grand_limits)     */
+#define GRAND_ECUDA (-3)       /* a CUDA runtime call failed; message has cudaGetErrorString          */
+
+/* edges per row tile: rows with more in-edges are split over several tiles (one warp each) */
+#define GRAND_TILE 64
+#define GRAND_MAX_HEADS 8
+#define GRAND_MAX_TERMS 8
+
+/* attention_type, reference src/function_transformer_attention.py:193-206 */
+enum grand_score_type {
+  GRAND_SCORE_SCALED_DOT = 0,  /* q.k / sqrt(d_k)                                   :195-196 */
+  GRAND_SCORE_COSINE = 1,      /* CosineSimilarity(eps=1e-5)                        :197-199 */
+  GRAND_SCORE_PEARSON = 2,     /* cosine of mean-centred q, k                       :200-206 */
+  GRAND_SCORE_EXP_KERNEL = 3,  /* ov^2 exp(-|q-k|^2 / (2 ls^2))                     :193-194 */
+  GRAND_SCORE_EXP_KERNEL2 = 4  /* beltrami: product of a feature and a positional exp kernel :133-169 */
+};
+
+/* normaliser, reference :210-213 and src/utils.py:179-208 */
+enum grand_norm_type {
+  GRAND_NORM_SOFTMAX = 0,      /* exp(s - max_seg) / (sum_seg + 1e-16), PyG softmax            */
+  GRAND_NORM_SQUAREPLUS = 1    /* o = s - max_GLOBAL; (o + sqrt(o^2 + 4))/2 / (sum_seg + 1e-16) */
+};
+
+/*
+ * The graph the ODE function owns (`odefunc.edge_index`, reference src/block_constant.py:24), re-laid out once:
+ * CSR by edge_index[0] (the row that torch_sparse.spmm sums into == the query node), stable so
+ * that edges of a row keep the caller's order, cut into row tiles of <= GRAND_TILE edges, plus a CSC view for
+ * attention_norm_idx = 1.  All arrays are device int32.  Built by the host mirror (graph_plan.py); the row ids may
+ * be a shard's local rows while `col` indexes the shard's [own | halo] feature rows (multi-GPU).
+ */
+typedef struct grand_graph {
+  int32_t n_rows;              /* rows to produce (nodes owned)                                       */
+  int32_t n_cols;              /* rows addressable through `col` (own + halo); == n_rows on one GPU   */
+  int32_t n_edges;             /* directed edges incl. self loops                                     */
+  int32_t n_tiles;             /* row tiles                                                           */
+  int32_t n_split_rows;        /* rows cut into more than one tile                                    */
+  int32_t n_split_tiles;       /* tiles belonging to split rows (they are the LAST n_split_tiles)     */
+  const int32_t* rowptr;       /* [n_rows + 1]                                                        */
+  const int32_t* col;          /* [n_edges] edge_index[1] in CSR order                                */
+  const int32_t* erow;         /* [n_edges] edge_index[0] in CSR order                                */
+  const int32_t* eid;          /* [n_edges] CSR position -> position in the caller's edge list        */
+  const int32_t* tile_row;     /* [n_tiles]                                                           */
+  const int32_t* tile_beg;     /* [n_tiles] first CSR position of the tile                            */
+  const int32_t* tile_split;   /* [n_tiles] -1, else index of the split row the tile belongs to       */
+  const int32_t* split_tile0;  /* [n_split_rows + 1] first split-tile slot of each split row          */
+  const int32_t* colptr;       /* [n_cols + 1] CSC by edge_index[1] (may be null if norm_idx 1 unused)*/
+  const int32_t* csc_pos;      /* [n_edges] CSC position -> CSR position                              */
+} grand_graph;
+
+/*
+ * Attention layer description == SpGraphTransAttentionLayer's state + opt
+ * (reference src/function_transformer_attention.py:59-126).  Weights are nn.Linear layout [out, in].
+ */
+typedef struct grand_attention {
+  int32_t d;                   /* in_features == state width (hidden_dim)                             */
+  int32_t ad;                  /* attention_dim                                                       */
+  int32_t heads;               /* opt['heads'], ad % heads == 0 (:80-81)                              */
+  int32_t score_type;          /* enum grand_score_type                                               */
+  int32_t norm_type;           /* enum grand_norm_type (opt['square_plus'])                           */
+  int32_t norm_idx;            /* opt['attention_norm_idx'] 0: segments share edge[0], 1: edge[1]     */
+  const float* wq;             /* Q.weight [ad, d]  (EXP_KERNEL2: block-diagonal [2 ad, d], see host)  */
+  const float* bq;             /* Q.bias   [ad]                                                       */
+  const float* wk;             /* K.weight [ad, d]                                                    */
+  const float* bk;             /* K.bias   [ad]                                                       */
+  const float* kernel_scalars; /* device [4]: output_var, lengthscale (, output_var_p, lengthscale_p) */
+  const float* edge_weight_csr;/* [n_edges] reweight_attention weights in CSR order, or null (:208-209)*/
+} grand_attention;
+
+/*
+ * What happens to the RHS value f_i once a row is finished -- the residual of
+ * reference src/function_transformer_attention.py:46-53 / src/function_laplacian_diffusion.py:43-51
+ *     f = alpha (ax - x) [+ beta x0],  alpha = sigmoid(*alpha_train) unless no_alpha_sigmoid
+ * fused with the Runge-Kutta stage combine torchdiffeq does in separate kernels (rk4_alt_step_func,
+ * _runge_kutta_step):   y_out = sum_t coef[t] * term[t] + coef_f * f.
+ */
+typedef struct grand_epilogue {
+  const float* alpha_train;    /* device scalar                                                       */
+  const float* beta_train;     /* device scalar (read only if x0 != null)                             */
+  const float* x0;             /* [n_rows, d] or null (opt['add_source'])                             */
+  int32_t no_alpha_sigmoid;
+  int32_t n_terms;             /* <= GRAND_MAX_TERMS                                                  */
+  float* f_out;                /* [n_rows, d] or null                                                 */
+  float* y_out;                /* [n_rows, d] or null                                                 */
+  float coef_f;
+  float coef[GRAND_MAX_TERMS];
+  const float* term[GRAND_MAX_TERMS];
+} grand_epilogue;
+
+/* caller-owned scratch; sizes from grand_workspace_sizes */
+typedef struct grand_workspace {
+  float* q;                    /* [n_rows, ad_eff]                                                    */
+  float* k;                    /* [n_cols, ad_eff]                                                    */
+  float* scores;               /* [n_edges, heads]   general path only                                */
+  float* seg_stats;            /* [n_cols, heads, 2] general path only: (max, sum) per segment        */
+  float* split_stats;          /* [n_split_tiles, heads, 2]                                           */
+  float* split_partial;        /* [n_split_tiles, d]                                                  */
+  int32_t* split_counter;      /* [n_split_rows], zero on first use; kernels leave it zero            */
+  float* gmax;                 /* [1] global max for squareplus (ordered-int encoded during reduction)*/
+} grand_workspace;
+
+int grand_abi_version(void);
+const char* grand_last_error(void);
+
+/* element counts of each workspace array for a graph / attention shape; any pointer may be null */
+int grand_workspace_sizes(const grand_graph* g, const grand_attention* a, int64_t* n_q, int64_t* n_k,
+                          int64_t* n_scores, int64_t* n_seg_stats, int64_t* n_split_stats,
+                          int64_t* n_split_partial, int64_t* n_split_counter);
+
+/* Q = x Wq^T + bq over n_rows rows, K = x Wk^T + bk over n_cols rows.
+ * Replaces the Q/K nn.Linear calls, reference src/function_transformer_attention.py:174-175 (V, :176, is unused on
+ * the mix_features=False path and is not computed). */
+int grand_project_qk(const float* x, int32_t n_rows, int32_t n_cols, const grand_attention* a, float* q, float* k,
+                     void* stream);
+
+/* One GRAND-nl RHS evaluation: ODEFuncTransformerAtt.forward (reference :38-53) = projection, per-edge scores,
+ * segment softmax / squareplus, head mean, (A (.) a) X aggregation, residual, RK stage combine.  Picks the fused
+ * single-pass kernel when the configuration allows it (norm_idx 0, softmax, heads <= GRAND_MAX_HEADS), the general
+ * scores -> segment-stats -> aggregate pipeline otherwise. */
+int grand_rhs_attention(const grand_graph* g, const grand_attention* a, const float* x, const grand_workspace* ws,
+                        const grand_epilogue* ep, void* stream);
+
+/* One GRAND-l RHS evaluation: LaplacianODEFunc.forward (reference src/function_laplacian_diffusion.py:38-51);
+ * `w_csr` is the per-edge weight sparse_multiply would use (:28-36) in CSR order. */
+int grand_rhs_laplacian(const grand_graph* g, int32_t d, const float* x, const float* w_csr, const grand_workspace* ws,
+                        const grand_epilogue* ep, void* stream);
+
+/* SpGraphTransAttentionLayer.forward (reference :128-214) as a standalone op: attention[E, H] and prods[E, H] in the
+ * CALLER's edge order (either may be null), and optionally the head-mean in CSR order for the Laplacian path
+ * (reference src/function_laplacian_diffusion.py:29-31). */
+int grand_attention_weights(const grand_graph* g, const grand_attention* a, const float* x, const grand_workspace* ws,
+                            float* attention_out, float* prods_out, float* mean_csr_out, void* stream);
+
+/* w_csr[p] = w[eid[p]] (heads == 1) or mean_h w[eid[p], h]: edge weights / frozen attention in caller order -> CSR. */
+int grand_edge_values_to_csr(const grand_graph* g, const float* w, int32_t heads, float* w_csr, void* stream);
+
+/* Fixed-grid integration, torchdiffeq FixedGridODESolver.integrate with method euler / midpoint / rk4 (= the 3/8
+ * rule rk4_alt_step_func; in-repo witness reference src/early_stop_solver.py:150-155,163-184).  `dt[n_steps]` are
+ * the host-side grid increments.  y (in: y(t0), out: y(t_end)) and 5 stage buffers of [n_rows, d] are caller-owned.
+ * a == null selects the Laplacian function with `w_csr`.  Every stage is one RHS launch whose epilogue writes the
+ * next stage's input; no axpy kernels. */
+enum grand_method { GRAND_EULER = 0, GRAND_MIDPOINT = 1, GRAND_RK4 = 2 };
+int grand_integrate_fixed(const grand_graph* g, const grand_attention* a, const float* w_csr, int32_t d,
+                          const grand_workspace* ws, const grand_epilogue* residual, int32_t method,
+                          const float* dt, int32_t n_steps, float* y, float* stage_buffers, void* stream);
+
+/* y_out = sum_t coef[t] * term[t]  (n elements); the dense-output / interpolation arithmetic of the solvers. */
+int grand_lincomb(int64_t n, int32_t n_terms, const float* const* term, const float* coef, float* y_out,
+                  void* stream);
+
+/* dopri5 error ratio: sum over elements of (err / (atol + rtol max(|y0|,|y1|)))^2 accumulated in double into
+ * *sumsq (caller zeroes it), err = sum_t coef[t] * k[t]   (torchdiffeq _compute_error_ratio with rms norm). */
+int grand_error_sumsq(int64_t n, int32_t n_terms, const float* const* k, const float* coef, const float* y0,
+                      const float* y1, float atol, float rtol, double* sumsq, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GRAND_B200_H_ */

@@ -1,0 +1,189 @@
+"""CPU-only tests: the C-ABI library loads and exports every symbol include/grand_b200.h declares (no compute calls),
+the host mirror's index plumbing, option handling, state_dict compatibility and loud failure without CUDA."""
+import copy
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+import _cases as C
+from __graft_entry__ import ROOT, load_package
+
+load_package()
+from graph_neural_pde_b200 import _native as N  # noqa: E402
+from graph_neural_pde_b200 import utils as U  # noqa: E402
+from graph_neural_pde_b200.block_constant import ConstantODEblock  # noqa: E402
+from graph_neural_pde_b200.block_transformer_attention import AttODEblock  # noqa: E402
+from graph_neural_pde_b200.engine import fixed_grid_dts  # noqa: E402
+from graph_neural_pde_b200.function_laplacian_diffusion import LaplacianODEFunc  # noqa: E402
+from graph_neural_pde_b200.function_transformer_attention import (ODEFuncTransformerAtt,  # noqa: E402
+                                                                   SpGraphTransAttentionLayer)
+from graph_neural_pde_b200.graph_plan import GraphPlan  # noqa: E402
+from graph_neural_pde_b200.model_configurations import (BlockNotDefined, FunctionNotDefined, set_block,  # noqa: E402
+                                                        set_function)
+from graph_neural_pde_b200.synthetic import Data, default_opt, make_graph  # noqa: E402
+from oracle import grand_oracle as O
+
+
+def test_library_exports_every_declared_symbol():
+  header = open(os.path.join(ROOT, 'include', 'grand_b200.h')).read()
+  declared = set(re.findall(r'^(?:int|const char\*)\s+(grand_[a-z0-9_]+)\s*\(', header, flags=re.M))
+  assert declared == set(N.SIGNATURES), declared ^ set(N.SIGNATURES)
+  assert os.path.exists(N.LIB_PATH), 'build the library first: python graph-neural-pde_b200/build_native.py'
+  handle = ctypes.CDLL(N.LIB_PATH)
+  for name in declared:
+    assert hasattr(handle, name), name
+  assert N.lib().grand_abi_version() == N.ABI_VERSION     # pure host call, no GPU needed
+  assert int(re.search(r'#define GRAND_TILE (\d+)', header).group(1)) == N.GRAND_TILE
+  assert int(re.search(r'#define GRAND_MAX_TERMS (\d+)', header).group(1)) == N.GRAND_MAX_TERMS
+  assert int(re.search(r'#define GRAND_MAX_HEADS (\d+)', header).group(1)) == N.GRAND_MAX_HEADS
+
+
+def test_argument_validation_happens_before_any_cuda_call():
+  g = N.GrandGraph()
+  g.n_rows, g.n_cols, g.n_edges, g.n_tiles = 4, 2, 0, 4     # n_cols < n_rows
+  ep = N.GrandEpilogue()
+  rc = N.lib().grand_rhs_laplacian(ctypes.byref(g), 8, 1, 1, None, ctypes.byref(ep), None)
+  assert rc == -1 and b'inconsistent sizes' in N.lib().grand_last_error()
+
+
+def test_graph_plan_invariants():
+  n = 300
+  ei = make_graph(n, 1500, max_degree=200, seed=1)
+  ei = torch.cat([ei, torch.stack([torch.arange(n), torch.arange(n)])], dim=1)     # loops appended at the end
+  p = GraphPlan(ei, n, device='cpu')
+  row, col = ei[0], ei[1]
+  eid = p.eid.long()
+  # CSR order is a stable sort by row
+  assert torch.equal(p.erow.long(), row[eid]) and torch.equal(p.col.long(), col[eid])
+  assert bool((p.erow[1:] >= p.erow[:-1]).all())
+  same_row = p.erow[1:] == p.erow[:-1]
+  assert bool((eid[1:][same_row] > eid[:-1][same_row]).all()), 'stable within a row'
+  deg = torch.bincount(row, minlength=n)
+  assert torch.equal(p.rowptr.long()[1:] - p.rowptr.long()[:-1], deg)
+  # tiles: cover every edge exactly once, <= GRAND_TILE edges, every row has a tile, split tiles first
+  covered = torch.zeros(p.n_edges, dtype=torch.int32)
+  rows_seen = torch.zeros(n, dtype=torch.int32)
+  for t in range(p.n_tiles):
+    r, b = int(p.tile_row[t]), int(p.tile_beg[t])
+    e = min(b + N.GRAND_TILE, int(p.rowptr[r + 1]))
+    assert int(p.rowptr[r]) <= b <= e
+    covered[b:e] += 1
+    rows_seen[r] += 1
+    s = int(p.tile_split[t])
+    assert (s >= 0) == (t < p.n_split_tiles)
+    if s >= 0:
+      assert int(p.split_tile0[s]) <= t < int(p.split_tile0[s + 1])
+  assert bool((covered == 1).all()) and bool((rows_seen >= 1).all())
+  assert int((deg > N.GRAND_TILE).sum()) == p.n_split_rows > 0
+  # CSC view
+  cpos = p.csc_pos.long()
+  assert bool((p.col.long()[cpos][1:] >= p.col.long()[cpos][:-1]).all())
+  assert torch.equal(torch.sort(cpos)[0], torch.arange(p.n_edges))
+  cdeg = torch.bincount(col, minlength=n)
+  assert torch.equal(p.colptr.long()[1:] - p.colptr.long()[:-1], cdeg)
+
+
+def test_plan_with_isolated_nodes_and_no_edges():
+  p = GraphPlan(torch.zeros((2, 0), dtype=torch.long), 5, device='cpu')
+  assert p.n_tiles == 5 and p.n_edges == 0 and p.n_split_tiles == 0
+  p = GraphPlan(torch.tensor([[0, 3], [3, 0]]), 6, device='cpu')
+  assert p.n_tiles == 6 and sorted(p.tile_row.tolist()) == list(range(6))
+
+
+def test_fixed_grid_matches_oracle_and_survey():
+  for T, h, steps in [(1.0, 0.1, 10), (18.294754260552843, 1, 19), (5.08, 1, 6), (1.6, 0.5, 4), (3.0, 1.0, 3)]:
+    dts, grid = fixed_grid_dts(0.0, T, h)
+    want = O.fixed_grid(0.0, T, h)
+    assert len(dts) == steps and torch.equal(grid, want)
+
+
+def test_graph_normalisation_matches_golden(golden):
+  for name, c in golden.items():
+    i = c['inputs']
+    if c['kind'] == 'get_rw_adj':
+      ei, ew = U.get_rw_adj(i['edge_index'], i['edge_weight'], i['norm_dim'], i['fill_value'], i['num_nodes'],
+                            dtype=torch.float32)
+    elif c['kind'] == 'gcn_norm_fill_val':
+      ei, ew = U.gcn_norm_fill_val(i['edge_index'], i['edge_weight'], i['fill_value'], i['num_nodes'],
+                                   dtype=torch.float32)
+    else:
+      continue
+    assert torch.equal(ei, c['outputs']['edge_index']), name
+    assert torch.equal(ew, c['outputs']['edge_weight']), name
+
+
+def test_state_dict_keys_match_reference(golden):
+  """Modules are constructible without a GPU; their state_dicts must load the reference's checkpoints strictly."""
+  dev = torch.device('cpu')
+  seen = 0
+  for name, c in golden.items():
+    if c['kind'] != 'block':
+      continue
+    opt = copy.deepcopy(c['opt'])
+    inp = c['inputs']
+    data = Data(x=inp['x'], edge_index=inp['edge_index'], edge_attr=inp['edge_attr'], num_nodes=inp['num_nodes'])
+    func_cls = set_function(opt)
+    block_cls = set_block(opt)
+    block = block_cls(func_cls, (), opt, data, dev, t=torch.tensor([0, opt['time']]))
+    block.load_state_dict(c['state_dict'], strict=True)
+    assert torch.equal(block.odefunc.edge_index, c['outputs']['odefunc_edge_index'])
+    C.assert_close(block.odefunc.edge_weight, c['outputs']['odefunc_edge_weight'], 1e-7, name)
+    seen += 1
+  assert seen >= 20
+
+
+def test_registry():
+  assert set_block({'block': 'constant'}) is ConstantODEblock and set_block({'block': 'attention'}) is AttODEblock
+  assert set_function({'function': 'laplacian'}) is LaplacianODEFunc
+  assert set_function({'function': 'transformer'}) is ODEFuncTransformerAtt
+  with pytest.raises(BlockNotDefined):
+    set_block({'block': 'nope'})
+  with pytest.raises(FunctionNotDefined):
+    set_function({'function': 'nope'})
+  with pytest.raises(NotImplementedError):
+    set_block({'block': 'hard_attention'})
+
+
+def test_heads_must_divide_attention_dim():
+  """reference test/test_attention_ode_block.py:51-56 relies on the AssertionError"""
+  opt = default_opt(heads=3, attention_dim=16)
+  with pytest.raises(AssertionError):
+    SpGraphTransAttentionLayer(8, 8, opt, torch.device('cpu'))
+
+
+def test_constant_init_and_attention_dim_fallback():
+  opt = default_opt(heads=2)
+  del opt['attention_dim']
+  layer = SpGraphTransAttentionLayer(6, 6, opt, torch.device('cpu'))
+  assert layer.attention_dim == 6 and layer.d_k == 3
+  assert torch.all(layer.Q.weight == 1e-5) and torch.all(layer.K.weight == 1e-5) and torch.all(layer.Wout.weight == 1e-5)
+
+
+def test_product_path_fails_loudly_without_cuda():
+  n, d = 10, 8
+  ei = make_graph(n, 20, seed=0)
+  opt = default_opt(function='transformer', hidden_dim=d, attention_dim=8, heads=2, method='rk4', step_size=1)
+  x = torch.randn(n, d)
+  data = Data(x=x, edge_index=ei, edge_attr=None, num_nodes=n)
+  block = ConstantODEblock(ODEFuncTransformerAtt, (), opt, data, torch.device('cpu'), t=torch.tensor([0, 1.0]))
+  block.eval()
+  block.set_x0(x)
+  with torch.no_grad():
+    with pytest.raises(N.GrandError, match='no CPU fallback'):
+      block.odefunc(0.0, x)
+    with pytest.raises(N.GrandError, match='no CPU fallback'):
+      block(x)
+
+
+def test_nfe_guard_counts_like_the_reference():
+  """`if nfe > max_nfe: raise` before the increment: max_nfe + 1 evaluations pass, the next one raises."""
+  opt = default_opt(function='laplacian', hidden_dim=4, max_nfe=5)
+  data = Data(x=torch.zeros(3, 4), edge_index=torch.tensor([[0, 1], [1, 0]]), edge_attr=None, num_nodes=3)
+  f = LaplacianODEFunc(4, 4, opt, data, torch.device('cpu'))
+  f._bump_nfe(6)
+  assert f.nfe == 6
+  with pytest.raises(U.MaxNFEException):
+    f._bump_nfe()
