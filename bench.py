@@ -1,0 +1,397 @@
+#!/usr/bin/env python
+"""bench.py -- ODE RHS throughput of the GRAND-nl hot path (BASELINE.json metric) on synthetic ogbn-arxiv-shaped input.
+
+    python bench.py --gpus 1 --steps 20 --warmup 3            # this repo's CUDA path
+    python bench.py --impl reference --steps 3 --warmup 1     # the reference's CPU path (oracle restatement)
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...   # node-partitioned, N > 1
+
+A "step" is one forward pass of the ODE block over the whole graph: rk4 (3/8 rule), T = 5.08, h = 1 -> 6 solver steps
+= 24 RHS evaluations (BASELINE.json configs[4]).  metric = edges*heads/s = E * H * evals / time.
+One JSON line on stdout (rank 0).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+  sys.path.insert(0, ROOT)
+
+METRIC = 'ODE RHS evals/sec (edges*heads/s)'
+UNIT = 'edges*heads/s'
+L2_MB = 126.0
+
+
+def measured_peaks():
+  path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+  if os.path.exists(path):
+    try:
+      return float(json.load(open(path))['hbm_gbs']), 'measured (MEASURED_PEAKS.json hbm_gbs)'
+    except Exception:
+      pass
+  return 6650.0, 'fallback (B200_PROFILING.md 6.65 TB/s)'
+
+
+def algorithmic_bytes(n, e, d, ad, add_source):
+  """compulsory traffic of one GRAND-nl RHS evaluation (int32 CSR, Q/K materialised once), split into
+  the projection kernel's share and the edge (dominant) kernel's share."""
+  proj = 4 * (n * d + 2 * n * ad)
+  edge = 4 * (2 * n * ad + n * d + n * d + (n * d if add_source else 0)) + 4 * e + 4 * (n + 1)
+  return proj, edge
+
+
+class ClockSampler:
+  """nvidia-smi clock / throttle-reason samples while the timed region runs (B200_PROFILING.md clocks line)."""
+  Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+       'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+  def __init__(self, index=0):
+    self.index, self.lines, self.proc = index, [], None
+
+  def __enter__(self):
+    try:
+      self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
+                                    '--format=csv,noheader,nounits', '-lms', '100'], stdout=subprocess.PIPE,
+                                   stderr=subprocess.DEVNULL, text=True)
+      self.thread = threading.Thread(target=self._read, daemon=True)
+      self.thread.start()
+    except Exception:
+      self.proc = None
+    return self
+
+  def _read(self):
+    for line in self.proc.stdout:
+      self.lines.append(line.strip())
+
+  def __exit__(self, *exc):
+    if self.proc is not None:
+      self.proc.terminate()
+      try:
+        self.proc.wait(timeout=2)
+      except Exception:
+        self.proc.kill()
+
+  def summary(self):
+    sm, mx, reasons = [], 0, set()
+    names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+    for line in self.lines:
+      parts = [p.strip() for p in line.split(',')]
+      if len(parts) < 7:
+        continue
+      try:
+        sm.append(float(parts[0]))
+        mx = max(mx, float(parts[1]))
+      except ValueError:
+        continue
+      for name, flag in zip(names, parts[3:7]):
+        if flag.lower().startswith('active'):
+          reasons.add(name)
+    sm.sort()
+    med = sm[len(sm) // 2] if sm else None
+    return {'sm_mhz': med, 'sm_max_mhz': mx or None, 'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+def build_workload(name, device, seed=0):
+  from __graft_entry__ import load_package
+  load_package()
+  from graph_neural_pde_b200.synthetic import SyntheticDataset, baseline_opt
+  ds = SyntheticDataset(name, seed=seed, num_features=8)   # features are not on the path; the state x is synthetic
+  key = {'ogbn-arxiv': 'C5', 'Cora': 'C2', 'Photo': 'C3'}[name]
+  opt = baseline_opt(key)
+  n = ds.data.num_nodes
+  g = torch.Generator().manual_seed(seed)
+  x = torch.randn(n, opt['hidden_dim'], generator=g)
+  return ds, opt, x
+
+
+def init_trained_like(block, seed=0):
+  """'trained-like' parameters (SURVEY.md 8(d) regime ii): W ~ N(0, 1/d), alpha_train = beta_train = 0."""
+  g = torch.Generator().manual_seed(seed)
+  with torch.no_grad():
+    for p in block.parameters():
+      if p.dim() == 2:
+        p.copy_((torch.randn(p.shape, generator=g) / p.shape[1] ** 0.5).to(p.device))
+
+
+def oracle_func(block_state, opt, edge_index, n, x0):
+  from oracle import grand_oracle as O
+  ei, ew = O.constant_block_graph(edge_index, None, n, opt, torch.float32)
+  alpha, beta = block_state['odefunc.alpha_train'], block_state['odefunc.beta_train']
+  prefix = 'odefunc.multihead_att_layer.'
+  P = {k[len(prefix):]: v for k, v in block_state.items() if k.startswith(prefix)}
+  return lambda t, y: O.transformer_rhs(y, ei, P, opt, alpha, beta, x0)
+
+
+def time_cpu_reference(func, x, h, n_rk4_steps, warmup, steps):
+  """Times `steps` samples, each = n_rk4_steps RK4 (3/8 rule) steps = 4 n RHS evals of the CPU oracle."""
+  from oracle import grand_oracle as O
+
+  def sample():
+    y = x
+    for _ in range(n_rk4_steps):
+      y = y + O.rk4_alt_step(func, 0.0, h, h, y)
+    return y
+
+  with torch.no_grad():
+    for _ in range(warmup):
+      sample()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+      sample()
+    dt = time.perf_counter() - t0
+  return dt / steps
+
+
+def run_reference(args, rank, world):
+  if rank != 0:
+    return
+  name = args.workload
+  ds, opt, x = build_workload(name, 'cpu')
+  from __graft_entry__ import load_package
+  load_package()
+  from graph_neural_pde_b200.block_constant import ConstantODEblock
+  from graph_neural_pde_b200.function_transformer_attention import ODEFuncTransformerAtt
+  from graph_neural_pde_b200.synthetic import Data
+  n = ds.data.num_nodes
+  data = Data(x=x, edge_index=ds.data.edge_index, edge_attr=None, num_nodes=n)
+  block = ConstantODEblock(ODEFuncTransformerAtt, (), opt, data, torch.device('cpu'), t=torch.tensor([0, opt['time']]))
+  init_trained_like(block)
+  state = {k: v.detach() for k, v in block.state_dict().items()}
+  func = oracle_func(state, opt, ds.data.edge_index, n, x)
+  threads = os.cpu_count() or 1
+  torch.set_num_threads(threads)
+  e = int(block.odefunc.edge_index.shape[1])
+  heads = opt['heads']
+  sec = time_cpu_reference(func, x, float(opt['step_size']), 1, args.warmup, args.steps)
+  value = e * heads * 4 / sec
+  line = {
+    'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
+    'warmup': args.warmup, 'ms_per_step': sec * 1e3, 'higher_is_better': True, 'scaling': 'strong',
+    'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+    'config': workload_config(name, opt, n, e, extra={'sample': '1 rk4 step = 4 RHS evals per step'}),
+    'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': threads, 'kind': 'port',
+                     'sample': 'each step = 1 rk4 (3/8) step = 4 RHS evals of the oracle restatement '
+                               '(torch CPU ops, all host threads); the reference itself cannot be imported: its '
+                               'third-party wheels are absent'},
+    'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+    'gpu_launches': 0,
+  }
+  print(json.dumps(line), flush=True)
+
+
+def workload_config(name, opt, n, e, extra=None):
+  cfg = {'workload': '%s GRAND-nl (transformer attention, %d heads, %s, T=%s, h=%s%s), synthetic Chung-Lu graph with '
+                     'the dataset\'s N/E/max-degree' % (name, opt['heads'], opt['method'], opt['time'],
+                                                        opt['step_size'], ', add_source' if opt['add_source'] else ''),
+         'nodes': n, 'edges_incl_self_loops': e, 'hidden_dim': opt['hidden_dim'], 'attention_dim': opt['attention_dim'],
+         'heads': opt['heads']}
+  cfg.update(extra or {})
+  return cfg
+
+
+def run_native_single(args):
+  from __graft_entry__ import load_package
+  load_package()
+  import ctypes as C
+  from graph_neural_pde_b200 import _native as N
+  from graph_neural_pde_b200.block_constant import ConstantODEblock
+  from graph_neural_pde_b200.engine import fixed_grid_dts
+  from graph_neural_pde_b200.function_transformer_attention import ODEFuncTransformerAtt
+  from graph_neural_pde_b200.odeint import NativeProblem
+  from graph_neural_pde_b200.synthetic import Data
+
+  dev = torch.device('cuda:0')
+  torch.cuda.set_device(dev)
+  name = args.workload
+  ds, opt, x_host = build_workload(name, dev)
+  n, d = x_host.shape
+  data = Data(x=x_host, edge_index=ds.data.edge_index, edge_attr=None, num_nodes=n)
+  block = ConstantODEblock(ODEFuncTransformerAtt, (), opt, data, dev, t=torch.tensor([0, opt['time']])).to(dev)
+  init_trained_like(block)
+  block.eval()
+  func = block.odefunc
+  e = int(func.edge_index.shape[1])
+  heads, ad = opt['heads'], opt['attention_dim']
+  dts, _ = fixed_grid_dts(0.0, opt['time'], opt['step_size'])
+  evals = 4 * len(dts)
+
+  x_pinned = x_host.pin_memory()
+  z_pinned = torch.empty_like(x_pinned).pin_memory()
+  x_dev = x_pinned.to(dev)
+
+  def step_resident():
+    func.nfe = 0   # run_GNN.py resets the NFE meters every epoch (reference src/run_GNN.py:90-95)
+    block.set_x0(x_dev)
+    with torch.no_grad():
+      return block(x_dev)
+
+  def step_e2e():
+    func.nfe = 0
+    x_dev.copy_(x_pinned, non_blocking=True)
+    block.set_x0(x_dev)
+    with torch.no_grad():
+      z = block(x_dev)
+    z_pinned.copy_(z, non_blocking=True)
+    return z
+
+  # launches per step, counted on one eager (non-graph) pass of exactly the launch sequence the graph replays
+  prob = NativeProblem(func, x_dev)
+  eng = prob.engine
+  ybuf = eng.buffer('y')
+  ybuf.copy_(x_dev)
+  before = N.lib().grand_launch_count()
+  eng.integrate_fixed(prob.spec, prob.w_csr, prob.epilogue(), 'rk4', dts, ybuf, use_graph=False)
+  launches_per_step = int(N.lib().grand_launch_count() - before)
+  torch.cuda.synchronize()
+
+  for _ in range(max(args.warmup, 3)):
+    step_resident()
+  torch.cuda.synchronize()
+
+  ev = lambda: torch.cuda.Event(enable_timing=True)
+  with ClockSampler(0) as clocks:
+    # ---- timed region 1: inputs resident in HBM ----
+    torch.cuda.synchronize()
+    a, b = ev(), ev()
+    a.record()
+    for _ in range(args.steps):
+      z = step_resident()
+    b.record()
+    torch.cuda.synchronize()
+    ms_step = a.elapsed_time(b) / args.steps
+    # ---- timed region 2: end to end through the block API from pinned host buffers ----
+    for _ in range(2):
+      step_e2e()
+    torch.cuda.synchronize()
+    a2, b2 = ev(), ev()
+    a2.record()
+    for _ in range(args.steps):
+      step_e2e()
+    b2.record()
+    torch.cuda.synchronize()
+    ms_e2e = a2.elapsed_time(b2) / args.steps
+    # ---- dominant kernel on its own: the fused edge kernel with the four rk4 stage epilogues ----
+    ws = eng.workspace(prob.spec)
+    n_planes = 5
+    stage = eng.buffer('stages', rows=n_planes * n)
+    yb, yc, k1, k2, k3 = (stage[i * n:(i + 1) * n] for i in range(5))
+    h = dts[0]
+    third = 1.0 / 3.0
+    stages = [
+      (ybuf, dict(f_out=k1, y_out=yb, coef_f=h * third, terms=[(ybuf, 1.0)])),
+      (yb, dict(f_out=k2, y_out=yc, coef_f=h, terms=[(ybuf, 1.0), (k1, -h * third)])),
+      (yc, dict(f_out=k3, y_out=yb, coef_f=h, terms=[(ybuf, 1.0), (k1, h), (k2, -h)])),
+      (yb, dict(y_out=yc, coef_f=h * 0.125, terms=[(ybuf, 1.0), (k1, h * 0.125), (k2, 3 * h * 0.125),
+                                                     (k3, 3 * h * 0.125)])),
+    ]
+    ybuf.copy_(x_dev)
+    eps = [(src, prob.epilogue(**kw)) for src, kw in stages]
+    lib = N.lib()
+    gs, as_ = C.byref(eng.plan.struct()), C.byref(prob.spec.struct)
+    stream = N.current_stream(dev)
+    N.check(lib.grand_project_qk(ybuf.data_ptr(), n, n, as_, ws.q, ws.k, stream))
+
+    def edge_pass():
+      for src, ep in eps:
+        N.check(lib.grand_rhs_attention_edges(gs, as_, src.data_ptr(), C.byref(ws), C.byref(ep), stream))
+
+    edge_pass()
+    torch.cuda.synchronize()
+    reps = 6
+    a3, b3 = ev(), ev()
+    a3.record()
+    for _ in range(reps):
+      edge_pass()
+    b3.record()
+    torch.cuda.synchronize()
+    edge_launches = reps * len(eps) * (2 if eng.plan.n_split_tiles > 0 else 1)
+    ms_edge_group = a3.elapsed_time(b3) / (reps * len(eps))   # fused kernel + its split-stats pre-pass
+    # projection alone
+    a4, b4 = ev(), ev()
+    a4.record()
+    for _ in range(reps * 4):
+      N.check(lib.grand_project_qk(ybuf.data_ptr(), n, n, as_, ws.q, ws.k, stream))
+    b4.record()
+    torch.cuda.synchronize()
+    ms_proj = a4.elapsed_time(b4) / (reps * 4)
+  clock_summary = clocks.summary()
+
+  peak, peak_src = measured_peaks()
+  proj_bytes, edge_bytes = algorithmic_bytes(n, e, d, ad, opt['add_source'])
+  achieved = edge_bytes / (ms_edge_group * 1e-3) / 1e9
+  traffic = None
+  tpath = os.path.join(ROOT, 'profiles', 'dominant_kernel_traffic.json')
+  if os.path.exists(tpath):
+    try:
+      traffic = json.load(open(tpath)).get('dram_bytes_per_launch')
+    except Exception:
+      traffic = None
+  working_set_mb = (4.0 * n * d * (1 + 1 + 5 + 1) + 8.0 * n * ad) / 1e6
+
+  # ---- CPU baseline: the oracle on this box's host cores, bounded sample ----
+  state = {k: v.detach().cpu() for k, v in block.state_dict().items()}
+  cpu_func = oracle_func(state, opt, ds.data.edge_index, n, x_host)
+  threads = os.cpu_count() or 1
+  torch.set_num_threads(threads)
+  sec = time_cpu_reference(cpu_func, x_host, float(opt['step_size']), 1, 1, 2)
+  cpu_value = e * heads * 4 / sec
+
+  value = e * heads * evals / (ms_step * 1e-3)
+  line = {
+    'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': 1, 'steps': args.steps, 'warmup': max(args.warmup, 3),
+    'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f32',
+    'data': 'synthetic',
+    'config': workload_config(name, opt, n, e, extra={
+      'rhs_evals_per_step': evals, 'us_per_rhs_eval': ms_step * 1e3 / evals,
+      'l2_policy': 'no flush: per-step working set %.0f MB (state, x0, 5 stage buffers, Q/K) > %.0f MB L2'
+                   % (working_set_mb, L2_MB),
+      'parallelism': 'single GPU', 'weights': 'trained-like N(0,1/d), seed 0'}),
+    'e2e': {'value': e * heads * evals / (ms_e2e * 1e-3), 'unit': UNIT, 'ms_per_step': ms_e2e,
+            'h2d_bytes_per_step': int(x_pinned.numel() * 4), 'd2h_bytes_per_step': int(z_pinned.numel() * 4)},
+    'gpu_launches': launches_per_step * args.steps,
+    'gpu_launches_per_step': launches_per_step,
+    'clocks': clock_summary,
+    'roofline': {'bound': 'hbm', 'kernel': 'rhs_kernel<MODE_FUSED,4,1> (+ split_tile_stats pre-pass)',
+                 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak, 'traffic': traffic,
+                 'peak_source': peak_src, 'algorithmic_bytes_per_launch': edge_bytes,
+                 'us_per_launch': ms_edge_group * 1e3, 'projection_us_per_launch': ms_proj * 1e3,
+                 'projection_algorithmic_bytes': proj_bytes,
+                 'projection_achieved_GBs': proj_bytes / (ms_proj * 1e-3) / 1e9,
+                 'rhs_eval_algorithmic_bytes': proj_bytes + edge_bytes,
+                 'rhs_eval_achieved_GBs': (proj_bytes + edge_bytes) / (ms_step * 1e-3 / evals) / 1e9},
+    'cpu_baseline': {'value': cpu_value, 'unit': UNIT, 'cores': threads, 'kind': 'port',
+                     'sample': '2 timed samples of 1 rk4 step = 4 RHS evals of the oracle (torch CPU ops)',
+                     'ms_per_rhs_eval': sec * 1e3 / 4},
+  }
+  print(json.dumps(line), flush=True)
+
+
+def run_native_multi(args, rank, world):
+  raise SystemExit('bench.py --gpus N > 1: the node-partitioned path is not wired into bench.py yet')
+
+
+def main():
+  ap = argparse.ArgumentParser()
+  ap.add_argument('--gpus', type=int, default=1)
+  ap.add_argument('--steps', type=int, default=20)
+  ap.add_argument('--warmup', type=int, default=3)
+  ap.add_argument('--impl', default='native', choices=['native', 'reference'])
+  ap.add_argument('--workload', default='ogbn-arxiv', choices=['ogbn-arxiv', 'Cora'])
+  args = ap.parse_args()
+  rank = int(os.environ.get('RANK', '0'))
+  world = int(os.environ.get('WORLD_SIZE', '1'))
+  if args.impl == 'reference':
+    return run_reference(args, rank, world)
+  if world > 1 or args.gpus > 1:
+    return run_native_multi(args, rank, world)
+  return run_native_single(args)
+
+
+if __name__ == '__main__':
+  main()

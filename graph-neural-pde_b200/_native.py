@@ -57,10 +57,13 @@ _P = C.c_void_p
 SIGNATURES = {
   'grand_abi_version': (C.c_int, []),
   'grand_last_error': (C.c_char_p, []),
+  'grand_launch_count': (C.c_int64, []),
   'grand_workspace_sizes': (C.c_int, [C.POINTER(GrandGraph), C.POINTER(GrandAttention)] + [C.POINTER(C.c_int64)] * 7),
   'grand_project_qk': (C.c_int, [_P, C.c_int32, C.c_int32, C.POINTER(GrandAttention), _P, _P, _P]),
   'grand_rhs_attention': (C.c_int, [C.POINTER(GrandGraph), C.POINTER(GrandAttention), _P, C.POINTER(GrandWorkspace),
                                      C.POINTER(GrandEpilogue), _P]),
+  'grand_rhs_attention_edges': (C.c_int, [C.POINTER(GrandGraph), C.POINTER(GrandAttention), _P,
+                                           C.POINTER(GrandWorkspace), C.POINTER(GrandEpilogue), _P]),
   'grand_rhs_laplacian': (C.c_int, [C.POINTER(GrandGraph), C.c_int32, _P, _P, C.POINTER(GrandWorkspace),
                                      C.POINTER(GrandEpilogue), _P]),
   'grand_attention_weights': (C.c_int, [C.POINTER(GrandGraph), C.POINTER(GrandAttention), _P,

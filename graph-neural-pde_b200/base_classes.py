@@ -145,7 +145,7 @@ class ODEblock(nn.Module):
     func, state = self.odefunc, x
     if self.opt["adjoint"] and self.training:
       state_dt = integrator(func, state, t, method=self.opt['method'], options=integrator_options,
-                            adjoint_method=self.opt['adjoint_method'], adjoint_options=adjoint_options,
+                            adjoint_method=self.opt['adjoint_method'], adjoint_options=adjoint_options(),
                             atol=self.atol, rtol=self.rtol, adjoint_atol=self.atol_adjoint,
                             adjoint_rtol=self.rtol_adjoint)
     else:

@@ -30,5 +30,5 @@ class ConstantODEblock(ODEblock):
 
   def forward(self, x):
     options = dict(step_size=self.opt['step_size'], max_iters=self.opt['max_iters'])
-    adjoint_options = dict(step_size=self.opt['adjoint_step_size'], max_iters=self.opt['max_iters'])
+    adjoint_options = lambda: dict(step_size=self.opt['adjoint_step_size'], max_iters=self.opt['max_iters'])
     return self._integrate(x, options, adjoint_options)

@@ -33,4 +33,5 @@ class AttODEblock(ODEblock):
   def forward(self, x):
     self.odefunc.attention_weights = self.get_attention_weights(x)
     self.reg_odefunc.odefunc.attention_weights = self.odefunc.attention_weights
-    return self._integrate(x, {'step_size': self.opt['step_size']}, {'step_size': self.opt['adjoint_step_size']})
+    return self._integrate(x, {'step_size': self.opt['step_size']},
+                           lambda: {'step_size': self.opt['adjoint_step_size']})

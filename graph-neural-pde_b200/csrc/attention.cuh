@@ -120,8 +120,15 @@ __device__ __forceinline__ float edge_score(const AttnView& a, const float* __re
   return 0.f;
 }
 
-// squareplus numerator of reference src/utils.py:196-198 given o = s - global_max
-__device__ __forceinline__ float squareplus_num(float o) { return (o + sqrtf(o * o + 4.f)) / 2.f; }
+// squareplus numerator of reference src/utils.py:196-198 given o = s - global_max (always <= 0).
+// (o + sqrt(o^2 + 4)) / 2 cancels catastrophically for o << 0: in fp32 the reference's own value carries a relative
+// error of up to ~ulp(|o|)/sp(o) (3e-5 at o = -30) that depends on the last bit of o.  The algebraically identical
+// 2 / (sqrt(o^2 + 4) - o) is accurate to fp32 rounding, i.e. it sits at the centre of the reference's error band,
+// which is the closest any independent implementation can get to it.
+__device__ __forceinline__ float squareplus_num(float o) {
+  const float r = sqrtf(fmaf(o, o, 4.f));
+  return o > 0.f ? 0.5f * (o + r) : 2.f / (r - o);
+}
 
 // numerator of the normaliser: exp(s - m_seg) (PyG softmax) or squareplus(s - gmax)
 __device__ __forceinline__ float norm_num(int norm_type, float s, float m) {

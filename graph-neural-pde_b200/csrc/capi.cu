@@ -8,6 +8,9 @@
 namespace grand {
 
 static thread_local char g_error[512] = "";
+static int64_t g_launches = 0;
+
+void count_launch(int n) { g_launches += n; }
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -97,6 +100,8 @@ extern "C" {
 
 int grand_abi_version(void) { return GRAND_ABI_VERSION; }
 
+int64_t grand_launch_count(void) { return g_launches; }
+
 const char* grand_last_error(void) { return g_error; }
 
 int grand_workspace_sizes(const grand_graph* g, const grand_attention* a, int64_t* n_q, int64_t* n_k,
@@ -130,6 +135,11 @@ int grand_rhs_attention(const grand_graph* g, const grand_attention* a, const fl
   return rhs_attention_impl(g, a, x, ws, ep, true, (cudaStream_t)stream);
 }
 
+int grand_rhs_attention_edges(const grand_graph* g, const grand_attention* a, const float* x, const grand_workspace* ws,
+                              const grand_epilogue* ep, void* stream) {
+  return rhs_attention_impl(g, a, x, ws, ep, false, (cudaStream_t)stream);
+}
+
 int grand_rhs_laplacian(const grand_graph* g, int32_t d, const float* x, const float* w_csr, const grand_workspace* ws,
                         const grand_epilogue* ep, void* stream) {
   return rhs_laplacian_impl(g, d, x, w_csr, ws, ep, (cudaStream_t)stream);
@@ -157,6 +167,7 @@ int grand_lincomb(int64_t n, int32_t n_terms, const float* const* term, const fl
     a.coef[t] = t < n_terms ? coef[t] : 0.f;
   }
   lincomb_kernel<<<elementwise_grid(n), 256, 0, (cudaStream_t)stream>>>(n, a, y_out);
+  count_launch();
   GRAND_CUDA_OK(cudaGetLastError());
   return GRAND_OK;
 }
@@ -173,6 +184,7 @@ int grand_error_sumsq(int64_t n, int32_t n_terms, const float* const* k, const f
     a.coef[t] = t < n_terms ? coef[t] : 0.f;
   }
   error_sumsq_kernel<<<elementwise_grid(n), 256, 0, (cudaStream_t)stream>>>(n, a, y0, y1, atol, rtol, sumsq);
+  count_launch();
   GRAND_CUDA_OK(cudaGetLastError());
   return GRAND_OK;
 }
@@ -254,7 +266,10 @@ int grand_integrate_fixed(const grand_graph* g, const grand_attention* a, const 
     float* tmp = cur; cur = nxt; nxt = tmp;
   }
   if (cur != y && n_steps > 0)
+  {
     GRAND_CUDA_OK(cudaMemcpyAsync(y, cur, plane * sizeof(float), cudaMemcpyDeviceToDevice, stream));
+    count_launch();
+  }
   return GRAND_OK;
 }
 

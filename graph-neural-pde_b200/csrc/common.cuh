@@ -12,6 +12,7 @@ constexpr int kWarp = 32;
 constexpr unsigned kFull = 0xffffffffu;
 
 void set_error(const char* fmt, ...);
+void count_launch(int n = 1);
 int cuda_fail(cudaError_t e, const char* what);
 
 #define GRAND_CUDA_OK(call)                                    \

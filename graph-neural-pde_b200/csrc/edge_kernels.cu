@@ -573,6 +573,7 @@ static int launch_rhs_mode(const RhsArgs& A, cudaStream_t stream) {
     else GRAND_REQUIRE(false, GRAND_EUNSUPPORTED, "state width %d (not a multiple of 4) > 256 is not built", d);
   }
   GRAND_CUDA_OK(cudaGetLastError());
+  count_launch();
   return GRAND_OK;
 }
 
@@ -592,16 +593,20 @@ static int run_general_prepass(const GraphView& g, const AttnView& a, const gran
   GRAND_REQUIRE(a.norm_idx == 0 || (g.colptr && g.csc_pos), GRAND_EINVAL,
                 "attention_norm_idx = 1 needs the CSC view (colptr / csc_pos)");
   const bool sp = a.norm_type == GRAND_NORM_SQUAREPLUS;
-  if (sp) init_gmax_kernel<<<1, 1, 0, stream>>>(ws->gmax);
+  if (sp) { init_gmax_kernel<<<1, 1, 0, stream>>>(ws->gmax); count_launch(); }
   if (g.n_edges > 0) {
     const int grid = (g.n_edges + 255) / 256;
     const bool vec4 = ((a.dk & 3) == 0) && ((a.ad_eff & 3) == 0);
     if (vec4) edge_scores_kernel<true><<<grid, 256, 0, stream>>>(g, a, ws->q, ws->k, ws->scores, sp ? ws->gmax : nullptr);
     else edge_scores_kernel<false><<<grid, 256, 0, stream>>>(g, a, ws->q, ws->k, ws->scores, sp ? ws->gmax : nullptr);
+    count_launch();
   }
-  if (sp) decode_gmax_kernel<<<1, 1, 0, stream>>>(ws->gmax);
+  if (sp) { decode_gmax_kernel<<<1, 1, 0, stream>>>(ws->gmax); count_launch(); }
   const int n_seg = a.norm_idx == 0 ? g.n_rows : g.n_cols;
-  if (n_seg > 0) segment_stats_kernel<<<(n_seg + 7) / 8, 256, 0, stream>>>(g, a, ws->scores, ws->gmax, ws->seg_stats);
+  if (n_seg > 0) {
+    segment_stats_kernel<<<(n_seg + 7) / 8, 256, 0, stream>>>(g, a, ws->scores, ws->gmax, ws->seg_stats);
+    count_launch();
+  }
   GRAND_CUDA_OK(cudaGetLastError());
   return GRAND_OK;
 }
@@ -636,6 +641,7 @@ int rhs_attention_impl(const grand_graph* g, const grand_attention* a, const flo
       if (vec4) split_tile_stats_kernel<true><<<grid, kWarpsPerBlock * kWarp, 0, stream>>>(A.g, A.a, ws->q, ws->k, ws->split_stats);
       else split_tile_stats_kernel<false><<<grid, kWarpsPerBlock * kWarp, 0, stream>>>(A.g, A.a, ws->q, ws->k, ws->split_stats);
       GRAND_CUDA_OK(cudaGetLastError());
+      count_launch();
     }
     return launch_rhs_mode<MODE_FUSED>(A, stream);
   }
@@ -680,6 +686,7 @@ int attention_weights_impl(const grand_graph* g, const grand_attention* a, const
     attention_out_kernel<<<(g->n_edges + 255) / 256, 256, 0, stream>>>(gv, av, ws->scores, ws->seg_stats, ws->gmax,
                                                                       attention_out, prods_out, mean_csr_out);
     GRAND_CUDA_OK(cudaGetLastError());
+    count_launch();
   }
   return GRAND_OK;
 }
@@ -691,6 +698,7 @@ int edge_values_to_csr_impl(const grand_graph* g, const float* w, int heads, flo
   if (g->n_edges > 0) {
     edge_values_to_csr_kernel<<<(g->n_edges + 255) / 256, 256, 0, stream>>>(view(g), w, heads, w_csr);
     GRAND_CUDA_OK(cudaGetLastError());
+    count_launch();
   }
   return GRAND_OK;
 }

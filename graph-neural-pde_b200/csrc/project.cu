@@ -135,6 +135,7 @@ int launch_project_qk(const float* x, int n_rows, int n_cols, int d, const float
   kern<<<grid, kProjThreads, smem, stream>>>(x, n_rows, n_cols, d, d4, ld, wq, bq, wk, bk, ad, tx_count,
                                              rows_per_tile, n_tiles, q, k);
   GRAND_CUDA_OK(cudaGetLastError());
+  count_launch();
   return GRAND_OK;
 }
 

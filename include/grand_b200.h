@@ -65,7 +65,7 @@ typedef struct grand_graph {
   int32_t n_edges;             /* directed edges incl. self loops                                     */
   int32_t n_tiles;             /* row tiles                                                           */
   int32_t n_split_rows;        /* rows cut into more than one tile                                    */
-  int32_t n_split_tiles;       /* tiles belonging to split rows (they are the LAST n_split_tiles)     */
+  int32_t n_split_tiles;       /* tiles of split rows; they are tiles [0, n_split_tiles), slot == tile */
   const int32_t* rowptr;       /* [n_rows + 1]                                                        */
   const int32_t* col;          /* [n_edges] edge_index[1] in CSR order                                */
   const int32_t* erow;         /* [n_edges] edge_index[0] in CSR order                                */
@@ -130,6 +130,8 @@ typedef struct grand_workspace {
 } grand_workspace;
 
 int grand_abi_version(void);
+/* number of kernel launches (and async copies) this library has issued so far in this process */
+int64_t grand_launch_count(void);
 const char* grand_last_error(void);
 
 /* element counts of each workspace array for a graph / attention shape; any pointer may be null */
@@ -149,6 +151,12 @@ int grand_project_qk(const float* x, int32_t n_rows, int32_t n_cols, const grand
  * scores -> segment-stats -> aggregate pipeline otherwise. */
 int grand_rhs_attention(const grand_graph* g, const grand_attention* a, const float* x, const grand_workspace* ws,
                         const grand_epilogue* ep, void* stream);
+
+/* The edge phase of grand_rhs_attention alone: ws->q / ws->k already hold the projections (grand_project_qk).  Used
+ * where a halo exchange sits between projection and aggregation (node-partitioned multi-GPU) and by bench.py to time
+ * the dominant kernel on its own. */
+int grand_rhs_attention_edges(const grand_graph* g, const grand_attention* a, const float* x, const grand_workspace* ws,
+                              const grand_epilogue* ep, void* stream);
 
 /* One GRAND-l RHS evaluation: LaplacianODEFunc.forward (reference src/function_laplacian_diffusion.py:38-51);
  * `w_csr` is the per-edge weight sparse_multiply would use (:28-36) in CSR order. */

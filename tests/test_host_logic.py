@@ -29,7 +29,7 @@ from oracle import grand_oracle as O
 
 def test_library_exports_every_declared_symbol():
   header = open(os.path.join(ROOT, 'include', 'grand_b200.h')).read()
-  declared = set(re.findall(r'^(?:int|const char\*)\s+(grand_[a-z0-9_]+)\s*\(', header, flags=re.M))
+  declared = set(re.findall(r'^(?:int|int64_t|const char\*)\s+(grand_[a-z0-9_]+)\s*\(', header, flags=re.M))
   assert declared == set(N.SIGNATURES), declared ^ set(N.SIGNATURES)
   assert os.path.exists(N.LIB_PATH), 'build the library first: python graph-neural-pde_b200/build_native.py'
   handle = ctypes.CDLL(N.LIB_PATH)
