@@ -241,6 +241,7 @@ def run_native_single(args):
     return z
 
   # launches per step, counted on one eager (non-graph) pass of exactly the launch sequence the graph replays
+  block.set_x0(x_dev)
   prob = NativeProblem(func, x_dev)
   eng = prob.engine
   ybuf = eng.buffer('y')
@@ -297,29 +298,39 @@ def run_native_single(args):
     stream = N.current_stream(dev)
     N.check(lib.grand_project_qk(ybuf.data_ptr(), n, n, as_, ws.q, ws.k, stream))
 
-    def edge_pass():
-      for src, ep in eps:
-        N.check(lib.grand_rhs_attention_edges(gs, as_, src.data_ptr(), C.byref(ws), C.byref(ep), stream))
+    def timed_graph(body, count):
+      """Replay `body` from a CUDA Graph (so host launch latency is not what is measured) and time it with events on
+      the replay stream; returns ms per launch group."""
+      body()
+      torch.cuda.synchronize()
+      graph = torch.cuda.CUDAGraph()
+      with torch.cuda.graph(graph):
+        st = N.current_stream(dev)
+        body(st)
+      graph.replay()
+      torch.cuda.synchronize()
+      e0, e1 = ev(), ev()
+      e0.record()
+      graph.replay()
+      e1.record()
+      torch.cuda.synchronize()
+      return e0.elapsed_time(e1) / count
 
-    edge_pass()
-    torch.cuda.synchronize()
     reps = 6
-    a3, b3 = ev(), ev()
-    a3.record()
-    for _ in range(reps):
-      edge_pass()
-    b3.record()
-    torch.cuda.synchronize()
-    edge_launches = reps * len(eps) * (2 if eng.plan.n_split_tiles > 0 else 1)
-    ms_edge_group = a3.elapsed_time(b3) / (reps * len(eps))   # fused kernel + its split-stats pre-pass
-    # projection alone
-    a4, b4 = ev(), ev()
-    a4.record()
-    for _ in range(reps * 4):
-      N.check(lib.grand_project_qk(ybuf.data_ptr(), n, n, as_, ws.q, ws.k, stream))
-    b4.record()
-    torch.cuda.synchronize()
-    ms_proj = a4.elapsed_time(b4) / (reps * 4)
+
+    def edge_body(st=None):
+      st = stream if st is None else st
+      for _ in range(reps):
+        for src, ep in eps:
+          N.check(lib.grand_rhs_attention_edges(gs, as_, src.data_ptr(), C.byref(ws), C.byref(ep), st))
+
+    def proj_body(st=None):
+      st = stream if st is None else st
+      for _ in range(reps * 4):
+        N.check(lib.grand_project_qk(ybuf.data_ptr(), n, n, as_, ws.q, ws.k, st))
+
+    ms_edge_group = timed_graph(edge_body, reps * len(eps))   # fused kernel + its split-stats pre-pass
+    ms_proj = timed_graph(proj_body, reps * 4)
   clock_summary = clocks.summary()
 
   peak, peak_src = measured_peaks()

@@ -24,12 +24,39 @@ project_qk_kernel(const float* __restrict__ x, int n_rows, int n_cols, int d, in
   const int tid = threadIdx.x;
   const int c4n = d4 >> 2;
 
-  // stage the weights once per CTA (zero padded to d4)
-  for (int idx = tid; idx < out * d4; idx += kProjThreads) {
-    const int o = idx / d4, c = idx - o * d4;
-    float v = 0.f;
-    if (c < d) v = (o < ad) ? wq[(size_t)o * d + c] : wk[(size_t)(o - ad) * d + c];
-    ws[o * ld + c] = v;
+  // stage the weights once per CTA (zero padded to d4); loads are batched ahead of the shared stores so that a CTA
+  // pays the L2 latency a few times, not once per element (this is what bounds the small graphs)
+  if ((d & 3) == 0) {
+    const int total = out * c4n;
+    constexpr int kBatch = 8;
+    for (int base = tid; base < total; base += kProjThreads * kBatch) {
+      float4 v[kBatch];
+#pragma unroll
+      for (int u = 0; u < kBatch; ++u) {
+        const int idx = base + u * kProjThreads;
+        v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (idx < total) {
+          const int o = idx / c4n, c4 = idx - o * c4n;
+          const float* src = (o < ad) ? wq + (size_t)o * d : wk + (size_t)(o - ad) * d;
+          v[u] = ldg4(src + 4 * c4);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < kBatch; ++u) {
+        const int idx = base + u * kProjThreads;
+        if (idx < total) {
+          const int o = idx / c4n, c4 = idx - o * c4n;
+          *reinterpret_cast<float4*>(ws + o * ld + 4 * c4) = v[u];
+        }
+      }
+    }
+  } else {
+    for (int idx = tid; idx < out * d4; idx += kProjThreads) {
+      const int o = idx / d4, c = idx - o * d4;
+      float v = 0.f;
+      if (c < d) v = (o < ad) ? wq[(size_t)o * d + c] : wk[(size_t)(o - ad) * d + c];
+      ws[o * ld + c] = v;
+    }
   }
 
   const int tx = tid % tx_count;

@@ -83,3 +83,22 @@ def oracle_block(case, dtype=torch.float32):
   counter[0] = 0
   z = O.block_forward(func, x, opt['time'], opt)
   return rhs, z, counter[0], (ei, ew)
+
+
+def exact_block_solution(case):
+  """z(T) of the case's ODE from a tight fp64 dopri5 run of the oracle (the arbiter for adaptive-solver parity)."""
+  holder = {}
+  real = O.block_forward
+
+  def capture(func, x, T, opt):
+    holder['f'] = func
+    return real(func, x, T, {**opt, 'method': 'euler', 'step_size': opt['time'] if opt['time'] > 0 else 1})
+
+  O.block_forward = capture
+  try:
+    oracle_block(case, torch.float64)
+  finally:
+    O.block_forward = real
+  x = case['inputs']['x'].double()
+  t = torch.tensor([0, case['opt']['time']], dtype=torch.float64)
+  return O.odeint_dopri5(holder['f'], x, t, 1e-13, 1e-13)[1]
