@@ -350,7 +350,10 @@ def run_native_single(args):
   cpu_func = oracle_func(state, opt, ds.data.edge_index, n, x_host)
   threads = os.cpu_count() or 1
   torch.set_num_threads(threads)
-  sec = time_cpu_reference(cpu_func, x_host, float(opt['step_size']), 1, 1, 2)
+  if args.skip_cpu:
+    sec = float('nan')
+  else:
+    sec = time_cpu_reference(cpu_func, x_host, float(opt['step_size']), 1, 1, 2)
   cpu_value = e * heads * 4 / sec
 
   value = e * heads * evals / (ms_step * 1e-3)
@@ -375,7 +378,8 @@ def run_native_single(args):
                  'projection_algorithmic_bytes': proj_bytes,
                  'projection_achieved_GBs': proj_bytes / (ms_proj * 1e-3) / 1e9,
                  'rhs_eval_algorithmic_bytes': proj_bytes + edge_bytes,
-                 'rhs_eval_achieved_GBs': (proj_bytes + edge_bytes) / (ms_step * 1e-3 / evals) / 1e9},
+                 'rhs_eval_achieved_GBs': (proj_bytes + edge_bytes) / (ms_step * 1e-3 / evals) / 1e9,
+                 'stage_mode': os.environ.get('GRAND_STAGE', 'default')},
     'cpu_baseline': {'value': cpu_value, 'unit': UNIT, 'cores': threads, 'kind': 'port',
                      'sample': '2 timed samples of 1 rk4 step = 4 RHS evals of the oracle (torch CPU ops)',
                      'ms_per_rhs_eval': sec * 1e3 / 4},
@@ -393,6 +397,7 @@ def main():
   ap.add_argument('--steps', type=int, default=20)
   ap.add_argument('--warmup', type=int, default=3)
   ap.add_argument('--impl', default='native', choices=['native', 'reference'])
+  ap.add_argument('--skip-cpu', action='store_true', help='skip the CPU baseline leg (kernel A/B runs)')
   ap.add_argument('--workload', default='ogbn-arxiv', choices=['ogbn-arxiv', 'Cora'])
   args = ap.parse_args()
   rank = int(os.environ.get('RANK', '0'))

@@ -11,7 +11,7 @@ import torch
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, 'libgrand_b200.so')
 
-GRAND_TILE = 64
+GRAND_TILE = 32
 GRAND_MAX_HEADS = 8
 GRAND_MAX_TERMS = 8
 ABI_VERSION = 1
@@ -28,7 +28,7 @@ class GrandGraph(C.Structure):
   _fields_ = [('n_rows', C.c_int32), ('n_cols', C.c_int32), ('n_edges', C.c_int32), ('n_tiles', C.c_int32),
               ('n_split_rows', C.c_int32), ('n_split_tiles', C.c_int32),
               ('rowptr', C.c_void_p), ('col', C.c_void_p), ('erow', C.c_void_p), ('eid', C.c_void_p),
-              ('tile_row', C.c_void_p), ('tile_beg', C.c_void_p), ('tile_split', C.c_void_p),
+              ('tile_row', C.c_void_p), ('tile_beg', C.c_void_p), ('tile_nrows', C.c_void_p), ('tile_split', C.c_void_p),
               ('split_tile0', C.c_void_p), ('colptr', C.c_void_p), ('csc_pos', C.c_void_p)]
 
 

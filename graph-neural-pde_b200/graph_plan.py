@@ -4,21 +4,55 @@
     (reference src/function_transformer_attention.py:190-191); a STABLE sort, so edges of a row
     keep the caller's relative order and `eid` maps every CSR position back to the caller's edge position
     (PyG appends self loops at the end of the list, so the caller's order is not sorted).
-  * row tiles of <= GRAND_TILE edges, one warp each; the tiles of rows that need several come first (their index
-    is their partial-sum slot), then one tile per remaining row in row order.  Every row has at least one tile,
-    also rows without edges (their output is -alpha x + beta x0).
+  * windows ("tiles") of <= GRAND_TILE edges, one warp each, one edge per lane: rows with more edges are cut into
+    chunks -- those tiles come first (their index is their partial-sum slot) --, the remaining rows are packed, in row
+    order, several whole rows to a window (<= max_rows).  Every row belongs to a tile, also rows without edges (their
+    output is -alpha x + beta x0).
   * CSC view (colptr, csc_pos) for attention_norm_idx = 1.
 
 Pure index plumbing in torch ops; works on CPU tensors too (host-logic tests), the kernels only ever see the
 device copy.
 """
+import numpy as np
 import torch
 
 from . import _native as N
 
 
+def pack_short_rows(deg, tile, max_rows):
+  """Greedy packing of consecutive short rows into windows: -> (first row, row count) per window (int64 arrays).
+  One pass over the degree array; rows with more than `tile` edges are skipped (they are chunked separately) and
+  close the current window, because a window covers a contiguous CSR range."""
+  n = len(deg)
+  first = np.empty(n, dtype=np.int64)
+  count = np.empty(n, dtype=np.int64)
+  w = 0
+  start, edges, rows = -1, 0, 0
+  d = deg.tolist()
+  for r in range(n):
+    dr = d[r]
+    if dr > tile:
+      if rows:
+        first[w], count[w] = start, rows
+        w += 1
+        rows = 0
+      continue
+    if rows and (edges + dr > tile or rows == max_rows):
+      first[w], count[w] = start, rows
+      w += 1
+      rows = 0
+    if rows == 0:
+      start, edges = r, 0
+    edges += dr
+    rows += 1
+  if rows:
+    first[w], count[w] = start, rows
+    w += 1
+  return first[:w].copy(), count[:w].copy()
+
+
 class GraphPlan:
-  def __init__(self, edge_index, num_nodes, device=None, num_cols=None, tile=N.GRAND_TILE):
+  def __init__(self, edge_index, num_nodes, device=None, num_cols=None, tile=N.GRAND_TILE, max_rows=8):
     assert edge_index.dim() == 2 and edge_index.shape[0] == 2, 'edge_index must be [2, E]'
     device = torch.device(device) if device is not None else edge_index.device
     ei = edge_index.to(device=device, dtype=torch.long)
@@ -36,7 +70,7 @@ class GraphPlan:
 
     n_tiles_of_row = torch.clamp((deg + tile - 1) // tile, min=1)
     split_rows = torch.nonzero(n_tiles_of_row > 1).flatten()
-    # longest rows first: their tiles are scheduled first and hide the tail
+    # longest rows first: their chunks are scheduled first and hide the tail
     if split_rows.numel() > 0:
       order = torch.argsort(deg[split_rows], descending=True, stable=True)
       split_rows = split_rows[order]
@@ -49,10 +83,15 @@ class GraphPlan:
     st_k = torch.arange(n_split_tiles, device=device) - split_tile0[:-1][st_split]
     st_row = split_rows[st_split]
     st_beg = rowptr[st_row] + st_k * tile
-    single_rows = torch.nonzero(n_tiles_of_row == 1).flatten()
-    tile_row = torch.cat([st_row, single_rows])
-    tile_beg = torch.cat([st_beg, rowptr[single_rows]])
-    tile_split = torch.cat([st_split, torch.full_like(single_rows, -1)])
+    # short rows (<= tile edges, also empty ones): consecutive rows are packed greedily into windows of <= tile
+    # edges and <= max_rows rows; a long row ends the current window
+    pr0, pn = pack_short_rows(deg.cpu().numpy(), tile, max_rows)
+    pack_row = torch.from_numpy(pr0).to(device)
+    pack_nrows = torch.from_numpy(pn).to(device)
+    tile_row = torch.cat([st_row, pack_row])
+    tile_beg = torch.cat([st_beg, rowptr[pack_row]])
+    tile_nrows = torch.cat([torch.ones_like(st_row), pack_nrows])
+    tile_split = torch.cat([st_split, torch.full_like(pack_row, -1)])
 
     col_csr = col[perm]
     perm_c = torch.argsort(col_csr, stable=True)
@@ -69,6 +108,7 @@ class GraphPlan:
     self.max_degree = int(deg.max()) if n_rows > 0 and e > 0 else 0
     self.rowptr, self.col, self.erow, self.eid = i32(rowptr), i32(col_csr), i32(row[perm]), i32(perm)
     self.tile_row, self.tile_beg, self.tile_split = i32(tile_row), i32(tile_beg), i32(tile_split)
+    self.tile_nrows = i32(tile_nrows)
     self.split_tile0 = i32(split_tile0)
     self.colptr, self.csc_pos = i32(colptr), i32(perm_c)
     self.eid_long = perm  # CSR position -> caller position (int64, for torch-side permutations)
@@ -80,8 +120,8 @@ class GraphPlan:
       g = N.GrandGraph()
       g.n_rows, g.n_cols, g.n_edges, g.n_tiles = self.n_rows, self.n_cols, self.n_edges, self.n_tiles
       g.n_split_rows, g.n_split_tiles = self.n_split_rows, self.n_split_tiles
-      for name in ('rowptr', 'col', 'erow', 'eid', 'tile_row', 'tile_beg', 'tile_split', 'split_tile0', 'colptr',
-                   'csc_pos'):
+      for name in ('rowptr', 'col', 'erow', 'eid', 'tile_row', 'tile_beg', 'tile_nrows', 'tile_split', 'split_tile0',
+                   'colptr', 'csc_pos'):
         setattr(g, name, getattr(self, name).data_ptr())
       self._struct = g
     return self._struct

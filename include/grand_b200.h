@@ -32,8 +32,9 @@ extern "C" {
 #define GRAND_EUNSUPPORTED (-2)/* shape outside what the kernels are built for (see grand_limits)     */
 #define GRAND_ECUDA (-3)       /* a CUDA runtime call failed; message has cudaGetErrorString          */
 
-/* edges per row tile: rows with more in-edges are split over several tiles (one warp each) */
-#define GRAND_TILE 64
+/* edges per window (one warp, one edge per lane): short rows are packed several to a window, rows with more
+ * in-edges are cut into chunks of this size */
+#define GRAND_TILE 32
 #define GRAND_MAX_HEADS 8
 #define GRAND_MAX_TERMS 8
 
@@ -70,8 +71,9 @@ typedef struct grand_graph {
   const int32_t* col;          /* [n_edges] edge_index[1] in CSR order                                */
   const int32_t* erow;         /* [n_edges] edge_index[0] in CSR order                                */
   const int32_t* eid;          /* [n_edges] CSR position -> position in the caller's edge list        */
-  const int32_t* tile_row;     /* [n_tiles]                                                           */
+  const int32_t* tile_row;     /* [n_tiles] first (or only) row of the tile                           */
   const int32_t* tile_beg;     /* [n_tiles] first CSR position of the tile                            */
+  const int32_t* tile_nrows;   /* [n_tiles] whole rows packed into the tile (1 for a chunk of a long row) */
   const int32_t* tile_split;   /* [n_tiles] -1, else index of the split row the tile belongs to       */
   const int32_t* split_tile0;  /* [n_split_rows + 1] first split-tile slot of each split row          */
   const int32_t* colptr;       /* [n_cols + 1] CSC by edge_index[1] (may be null if norm_idx 1 unused)*/

@@ -43,7 +43,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_argument_validation_happens_before_any_cuda_call():
   g = N.GrandGraph()
-  g.n_rows, g.n_cols, g.n_edges, g.n_tiles = 4, 2, 0, 4     # n_cols < n_rows
+  g.n_rows, g.n_cols, g.n_edges, g.n_tiles = 4, 2, 0, 1     # n_cols < n_rows
   ep = N.GrandEpilogue()
   rc = N.lib().grand_rhs_laplacian(ctypes.byref(g), 8, 1, 1, None, ctypes.byref(ep), None)
   assert rc == -1 and b'inconsistent sizes' in N.lib().grand_last_error()
@@ -63,20 +63,26 @@ def test_graph_plan_invariants():
   assert bool((eid[1:][same_row] > eid[:-1][same_row]).all()), 'stable within a row'
   deg = torch.bincount(row, minlength=n)
   assert torch.equal(p.rowptr.long()[1:] - p.rowptr.long()[:-1], deg)
-  # tiles: cover every edge exactly once, <= GRAND_TILE edges, every row has a tile, split tiles first
+  # tiles: cover every edge exactly once, <= GRAND_TILE edges, every row in exactly one packed window or in the
+  # chunks of its long row, chunk tiles first
   covered = torch.zeros(p.n_edges, dtype=torch.int32)
   rows_seen = torch.zeros(n, dtype=torch.int32)
   for t in range(p.n_tiles):
-    r, b = int(p.tile_row[t]), int(p.tile_beg[t])
-    e = min(b + N.GRAND_TILE, int(p.rowptr[r + 1]))
-    assert int(p.rowptr[r]) <= b <= e
-    covered[b:e] += 1
-    rows_seen[r] += 1
-    s = int(p.tile_split[t])
+    r, b, nr, s = int(p.tile_row[t]), int(p.tile_beg[t]), int(p.tile_nrows[t]), int(p.tile_split[t])
     assert (s >= 0) == (t < p.n_split_tiles)
     if s >= 0:
-      assert int(p.split_tile0[s]) <= t < int(p.split_tile0[s + 1])
-  assert bool((covered == 1).all()) and bool((rows_seen >= 1).all())
+      assert nr == 1 and int(p.split_tile0[s]) <= t < int(p.split_tile0[s + 1])
+      e = min(b + N.GRAND_TILE, int(p.rowptr[r + 1]))
+      assert int(p.rowptr[r]) <= b < e
+      rows_seen[r] = 1
+    else:
+      assert 1 <= nr <= 8 and b == int(p.rowptr[r])
+      e = int(p.rowptr[r + nr])
+      assert e - b <= N.GRAND_TILE
+      assert bool((rows_seen[r:r + nr] == 0).all())
+      rows_seen[r:r + nr] += 1
+    covered[b:e] += 1
+  assert bool((covered == 1).all()) and bool((rows_seen == 1).all())
   assert int((deg > N.GRAND_TILE).sum()) == p.n_split_rows > 0
   # CSC view
   cpos = p.csc_pos.long()
@@ -88,9 +94,9 @@ def test_graph_plan_invariants():
 
 def test_plan_with_isolated_nodes_and_no_edges():
   p = GraphPlan(torch.zeros((2, 0), dtype=torch.long), 5, device='cpu')
-  assert p.n_tiles == 5 and p.n_edges == 0 and p.n_split_tiles == 0
+  assert int(p.tile_nrows.sum()) == 5 and p.n_edges == 0 and p.n_split_tiles == 0
   p = GraphPlan(torch.tensor([[0, 3], [3, 0]]), 6, device='cpu')
-  assert p.n_tiles == 6 and sorted(p.tile_row.tolist()) == list(range(6))
+  assert int(p.tile_nrows.sum()) == 6 and p.n_tiles == 1
 
 
 def test_fixed_grid_matches_oracle_and_survey():
