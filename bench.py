@@ -388,7 +388,120 @@ def run_native_single(args):
 
 
 def run_native_multi(args, rank, world):
-  raise SystemExit('bench.py --gpus N > 1: the node-partitioned path is not wired into bench.py yet')
+  """N > 1: 1-D node partition of the same workload over the ranks (strong scaling), halo exchange of boundary rows
+  every RHS evaluation over NCCL.  Timing: barrier + synchronize on both sides, CUDA events, MAX over ranks."""
+  import torch.distributed as dist
+  from __graft_entry__ import load_package
+  load_package()
+  from graph_neural_pde_b200 import _native as N
+  from graph_neural_pde_b200.block_constant import ConstantODEblock
+  from graph_neural_pde_b200.distributed import ShardedTransformerRHS
+  from graph_neural_pde_b200.engine import fixed_grid_dts
+  from graph_neural_pde_b200.function_transformer_attention import ODEFuncTransformerAtt
+  from graph_neural_pde_b200.synthetic import Data
+
+  local_rank = int(os.environ.get('LOCAL_RANK', rank))
+  dev = torch.device('cuda', local_rank)
+  torch.cuda.set_device(dev)
+  if not dist.is_initialized():
+    dist.init_process_group('nccl', device_id=dev)
+  name = args.workload
+  ds, opt, x_host = build_workload(name, dev)      # same seed on every rank: replicated graph and parameters
+  n, d = x_host.shape
+  data = Data(x=x_host, edge_index=ds.data.edge_index, edge_attr=None, num_nodes=n)
+  block = ConstantODEblock(ODEFuncTransformerAtt, (), opt, data, dev, t=torch.tensor([0, opt['time']])).to(dev)
+  init_trained_like(block)
+  block.eval()
+  func = block.odefunc
+  e = int(func.edge_index.shape[1])
+  heads, ad = opt['heads'], opt['attention_dim']
+  dts, _ = fixed_grid_dts(0.0, opt['time'], opt['step_size'])
+  evals = 4 * len(dts)
+  shard = ShardedTransformerRHS(func, n, dev)
+  part = shard.part
+  x_pinned = x_host[part.r0:part.r1].contiguous().pin_memory()
+  z_pinned = torch.empty_like(x_pinned).pin_memory()
+  x_dev = x_pinned.to(dev)
+
+  def step_resident():
+    func.nfe = 0
+    with torch.no_grad():
+      return shard.forward_block(x_dev, x_dev, opt)
+
+  def step_e2e():
+    func.nfe = 0
+    x_dev.copy_(x_pinned, non_blocking=True)
+    with torch.no_grad():
+      z = shard.forward_block(x_dev, x_dev, opt)
+    z_pinned.copy_(z, non_blocking=True)
+
+  before = N.lib().grand_launch_count()
+  step_resident()
+  launches_per_step = int(N.lib().grand_launch_count() - before)
+  for _ in range(max(args.warmup, 3)):
+    step_resident()
+
+  def timed(fn):
+    torch.cuda.synchronize()
+    dist.barrier()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(args.steps):
+      fn()
+    b.record()
+    torch.cuda.synchronize()
+    dist.barrier()
+    ms = torch.tensor([a.elapsed_time(b) / args.steps], device=dev)
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    return float(ms.item())
+
+  with ClockSampler(local_rank) as clocks:
+    ms_step = timed(step_resident)
+    step_e2e()
+    ms_e2e = timed(step_e2e)
+  clock_summary = clocks.summary()
+
+  summaries = [None] * world
+  dist.all_gather_object(summaries, part.summary())
+  launches = torch.tensor([launches_per_step], device=dev)
+  dist.all_reduce(launches, op=dist.ReduceOp.SUM)
+  if rank == 0:
+    peak, peak_src = measured_peaks()
+    proj_bytes, edge_bytes = algorithmic_bytes(n, e, d, ad, opt['add_source'])
+    halo_bytes = sum(s['halo_rows'] for s in summaries) * d * 4
+    per_eval_s = ms_step * 1e-3 / evals
+    line = {
+      'metric': METRIC, 'value': e * heads * evals / (ms_step * 1e-3), 'unit': UNIT, 'n_gpus': world,
+      'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': ms_step, 'higher_is_better': True,
+      'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+      'config': workload_config(name, opt, n, e, extra={
+        'rhs_evals_per_step': evals, 'us_per_rhs_eval': ms_step * 1e3 / evals,
+        'parallelism': 'np%d: 1-D node partition balanced by edges, halo rows exchanged per RHS eval '
+                       '(NCCL all-to-all-v)' % world,
+        'halo_rows_per_rank': [s['halo_rows'] for s in summaries],
+        'halo_fraction_of_graph_per_rank': [round(s['halo_fraction_of_graph'], 4) for s in summaries],
+        'edges_per_rank': [s['edges'] for s in summaries],
+        'halo_bytes_per_rhs_eval_all_ranks': halo_bytes,
+        'l2_policy': 'no flush: per-rank working set >= %.0f MB > %.0f MB L2'
+                     % (4.0 * (n / world) * d * 8 / 1e6 + halo_bytes / world / 1e6, L2_MB),
+        'weights': 'trained-like N(0,1/d), seed 0'}),
+      'e2e': {'value': e * heads * evals / (ms_e2e * 1e-3), 'unit': UNIT, 'ms_per_step': ms_e2e,
+              'h2d_bytes_per_step': int(n * d * 4), 'd2h_bytes_per_step': int(n * d * 4)},
+      'gpu_launches': int(launches.item()) * args.steps, 'gpu_launches_per_step_all_ranks': int(launches.item()),
+      'clocks': clock_summary,
+      'roofline': {'bound': 'hbm', 'kernel': 'whole RHS evaluation across %d GPUs (projection + fused edge kernel + '
+                                             'halo pack/exchange)' % world,
+                   'achieved': (proj_bytes + edge_bytes) / per_eval_s / 1e9, 'peak': peak * world, 'unit': 'GB/s',
+                   'frac': (proj_bytes + edge_bytes) / per_eval_s / 1e9 / (peak * world), 'traffic': None,
+                   'peak_source': peak_src + ' x n_gpus',
+                   'algorithmic_bytes_per_launch': proj_bytes + edge_bytes,
+                   'nvlink_bytes_per_rhs_eval': halo_bytes,
+                   'nvlink_time_floor_us_per_eval': max(s['halo_rows'] for s in summaries) * d * 4 / 770e9 * 1e6},
+    }
+    print(json.dumps(line), flush=True)
+  dist.barrier()
+  dist.destroy_process_group()
 
 
 def main():

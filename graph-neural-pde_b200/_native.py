@@ -72,6 +72,7 @@ SIGNATURES = {
   'grand_integrate_fixed': (C.c_int, [C.POINTER(GrandGraph), C.POINTER(GrandAttention), _P, C.c_int32,
                                        C.POINTER(GrandWorkspace), C.POINTER(GrandEpilogue), C.c_int32,
                                        c_float_p, C.c_int32, _P, _P, _P]),
+  'grand_pack_rows': (C.c_int, [_P, _P, C.c_int64, C.c_int32, _P, _P]),
   'grand_lincomb': (C.c_int, [C.c_int64, C.c_int32, C.POINTER(C.c_void_p), c_float_p, _P, _P]),
   'grand_error_sumsq': (C.c_int, [C.c_int64, C.c_int32, C.POINTER(C.c_void_p), c_float_p, _P, _P, C.c_float,
                                    C.c_float, _P, _P]),

@@ -86,6 +86,22 @@ error_sumsq_kernel(int64_t n, ErrArgs a, const float* __restrict__ y0, const flo
   }
 }
 
+__global__ void __launch_bounds__(256)
+pack_rows_kernel(const float* __restrict__ x, const int* __restrict__ idx, int64_t n_idx, int d,
+                 float* __restrict__ out) {
+  // one warp per row, 128-bit lanes when the row width allows it
+  const int lane = threadIdx.x & 31;
+  const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (r >= n_idx) return;
+  const float* src = x + (size_t)__ldg(idx + r) * d;
+  float* dst = out + (size_t)r * d;
+  if ((d & 3) == 0) {
+    for (int c = lane * 4; c < d; c += 128) st_stream4(dst + c, ldg4(src + c));
+  } else {
+    for (int c = lane; c < d; c += 32) dst[c] = __ldg(src + c);
+  }
+}
+
 static int elementwise_grid(int64_t n) {
   int64_t blocks = (n + 255) / 256;
   const int64_t cap = (int64_t)num_sms() * 8;
@@ -153,6 +169,15 @@ int grand_attention_weights(const grand_graph* g, const grand_attention* a, cons
 
 int grand_edge_values_to_csr(const grand_graph* g, const float* w, int32_t heads, float* w_csr, void* stream) {
   return edge_values_to_csr_impl(g, w, heads, w_csr, (cudaStream_t)stream);
+}
+
+int grand_pack_rows(const float* x, const int32_t* idx, int64_t n_idx, int32_t d, float* out, void* stream) {
+  GRAND_REQUIRE(n_idx >= 0 && d > 0 && (n_idx == 0 || (x && idx && out)), GRAND_EINVAL, "pack_rows: bad argument");
+  if (n_idx == 0) return GRAND_OK;
+  pack_rows_kernel<<<(unsigned)((n_idx + 7) / 8), 256, 0, (cudaStream_t)stream>>>(x, idx, n_idx, d, out);
+  GRAND_CUDA_OK(cudaGetLastError());
+  count_launch();
+  return GRAND_OK;
 }
 
 int grand_lincomb(int64_t n, int32_t n_terms, const float* const* term, const float* coef, float* y_out,

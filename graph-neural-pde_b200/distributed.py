@@ -1,0 +1,226 @@
+"""Node-partitioned multi-GPU RHS / integration for graphs large enough to shard (ogbn-arxiv), SURVEY.md 8(e).
+
+One process per GPU (`torch.distributed`, NCCL).  Rows of the state X are split into P contiguous ranges balanced by
+edge count; rank p owns the CSR rows (all in-edges of its query nodes), so the attention softmax (attention_norm_idx
+0) and the aggregation are local.  What is not local are the neighbour rows X_j owned by other ranks -- the HALO.
+Per RHS evaluation:
+
+    1. pack the own rows other ranks need (grand_pack_rows) and exchange them (NCCL all-to-all-v; the receive buffer
+       IS the halo section of the local state, laid out [own rows | halo rows grouped by owner]),
+    2. project Q for the own rows and K for own + halo rows (K_j of a halo row is recomputed locally: ad*d MACs
+       instead of shipping ad more floats),
+    3. run the fused edge kernel over the local graph; its epilogue writes the next stage's own rows.
+
+The reference has no distributed path at all; this is new design.  Everything that decides WHO owns
+WHAT is plain index arithmetic and is exercised on CPU with gloo (tests/test_distributed_cpu.py).
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import _native as N
+from .engine import RhsEngine, fixed_grid_dts
+from .graph_plan import GraphPlan
+
+
+def balanced_row_ranges(deg, world):
+  """Contiguous row ranges with ~equal edge counts: boundaries at the quantiles of the cumulative degree
+  (+1 per row so that empty rows still cost something)."""
+  work = np.cumsum(np.asarray(deg, dtype=np.int64) + 1)
+  total = int(work[-1]) if len(work) else 0
+  bounds = [0]
+  for p in range(1, world):
+    bounds.append(int(np.searchsorted(work, total * p / world, side='right')))
+  bounds.append(len(deg))
+  for p in range(1, len(bounds)):
+    bounds[p] = max(bounds[p], bounds[p - 1])
+  return bounds
+
+
+class Partition:
+  """Everything rank `rank` of `world` needs to know about the shard layout; computed identically on every rank from
+  the full (row, col) edge list -- no communication at set-up."""
+
+  def __init__(self, edge_index, num_nodes, world, rank):
+    ei = edge_index.cpu()
+    row, col = ei[0].numpy(), ei[1].numpy()
+    n = int(num_nodes)
+    deg = np.bincount(row, minlength=n)
+    self.world, self.rank, self.n = world, rank, n
+    self.bounds = balanced_row_ranges(deg, world)
+    owner_of = np.empty(n, dtype=np.int64)
+    for p in range(world):
+      owner_of[self.bounds[p]:self.bounds[p + 1]] = p
+    self.owner_of = owner_of
+    self.r0, self.r1 = self.bounds[rank], self.bounds[rank + 1]
+    self.n_own = self.r1 - self.r0
+
+    def needs(p):
+      """sorted global ids that rank p's rows reference but p does not own"""
+      mine = (row >= self.bounds[p]) & (row < self.bounds[p + 1])
+      cols = np.unique(col[mine])
+      return cols[(cols < self.bounds[p]) | (cols >= self.bounds[p + 1])]
+
+    # my halo, grouped by owner (np.unique is sorted and owners are contiguous ranges => already grouped)
+    halo = needs(rank)
+    self.halo_global = halo
+    self.n_halo = len(halo)
+    halo_owner = owner_of[halo] if len(halo) else np.empty(0, dtype=np.int64)
+    self.recv_counts = [int((halo_owner == p).sum()) for p in range(world)]
+    # what every peer needs from me (local row indices, in the order the peer expects them: sorted by global id)
+    send_idx, self.send_counts = [], []
+    for p in range(world):
+      if p == rank:
+        self.send_counts.append(0)
+        continue
+      want = needs(p)
+      want = want[(want >= self.r0) & (want < self.r1)]
+      send_idx.append(want - self.r0)
+      self.send_counts.append(len(want))
+    self.send_index = np.concatenate(send_idx) if send_idx else np.empty(0, dtype=np.int64)
+
+    # local graph: rows -> [0, n_own), cols -> own index or n_own + position in halo
+    mine = (row >= self.r0) & (row < self.r1)
+    lrow = row[mine] - self.r0
+    gcol = col[mine]
+    own_col = (gcol >= self.r0) & (gcol < self.r1)
+    lcol = np.where(own_col, gcol - self.r0, 0)
+    if self.n_halo:
+      lcol = np.where(own_col, lcol, self.n_own + np.searchsorted(halo, gcol))
+    self.local_edge_index = torch.from_numpy(np.stack([lrow, lcol])).long()
+    self.local_edge_ids = torch.from_numpy(np.nonzero(mine)[0]).long()   # positions in the caller's edge list
+    self.n_local_edges = int(mine.sum())
+
+  @property
+  def n_cols(self):
+    return self.n_own + self.n_halo
+
+  def summary(self):
+    return {'rank': self.rank, 'rows': self.n_own, 'edges': self.n_local_edges, 'halo_rows': self.n_halo,
+            'halo_fraction_of_graph': self.n_halo / max(1, self.n), 'send_rows': int(sum(self.send_counts))}
+
+
+def exchange_halo(send_buf, recv_buf, send_counts, recv_counts, group=None):
+  """All-to-all-v of row blocks.  NCCL: one all_to_all_single; gloo (CPU tests) has no all-to-all: paired
+  isend / irecv."""
+  world = dist.get_world_size(group)
+  if dist.get_backend(group) == 'nccl':
+    dist.all_to_all_single(recv_buf, send_buf, output_split_sizes=recv_counts, input_split_sizes=send_counts,
+                           group=group)
+    return
+  rank = dist.get_rank(group)
+  ops, so, ro = [], 0, 0
+  for p in range(world):
+    if p != rank and send_counts[p]:
+      ops.append(dist.P2POp(dist.isend, send_buf[so:so + send_counts[p]], p, group))
+    so += send_counts[p]
+    if p != rank and recv_counts[p]:
+      ops.append(dist.P2POp(dist.irecv, recv_buf[ro:ro + recv_counts[p]], p, group))
+    ro += recv_counts[p]
+  if ops:
+    for req in dist.batch_isend_irecv(ops):
+      req.wait()
+
+
+class ShardedTransformerRHS:
+  """GRAND-nl on a node partition: the device side of one rank.  `func` is this package's ODEFuncTransformerAtt built
+  over the FULL graph (its parameters are replicated on every rank, like DDP); this object owns the rank's local plan,
+  state buffers and the stage driver."""
+
+  def __init__(self, func, num_nodes, device, group=None):
+    self.func = func
+    self.group = group
+    self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+    self.device = torch.device(device)
+    self.part = Partition(func.edge_index, num_nodes, self.world, self.rank)
+    p = self.part
+    self.d = int(func.in_features)
+    self.plan = GraphPlan(p.local_edge_index, num_nodes=p.n_own, device=self.device, num_cols=p.n_cols)
+    self.engine = RhsEngine(self.plan, self.d)
+    self.send_index = torch.from_numpy(p.send_index).to(self.device, torch.int32)
+    self.send_buf = torch.empty((max(len(p.send_index), 1), self.d), dtype=torch.float32, device=self.device)
+    opt = func.opt
+    if not (opt['attention_norm_idx'] == 0 and not opt['square_plus']):
+      raise NotImplementedError('the sharded path needs row-local normalisation (attention_norm_idx 0, softmax); '
+                                'column statistics would need an extra all-reduce (SURVEY.md 8(e))')
+    if opt['reweight_attention'] and func.multihead_att_layer.edge_weights is not None:
+      raise NotImplementedError('reweight_attention is not wired into the sharded path')
+    self.spec = func.multihead_att_layer.spec(self.engine)
+    self.ws = self.engine.workspace(self.spec)
+    self._bufs = {}
+
+  # ---- buffers: [n_cols, d] with the own rows first ---------------------------------------------------------
+  def buffer(self, name):
+    t = self._bufs.get(name)
+    if t is None:
+      t = torch.zeros((self.part.n_cols, self.d), dtype=torch.float32, device=self.device)
+      self._bufs[name] = t
+    return t
+
+  def own(self, t):
+    return t[:self.part.n_own]
+
+  def scatter_global(self, x_global, name):
+    """local buffer <- my rows of a global [N, d] tensor (set-up / tests)"""
+    buf = self.buffer(name)
+    self.own(buf).copy_(x_global[self.part.r0:self.part.r1].to(self.device))
+    return buf
+
+  # ---- one RHS evaluation -------------------------------------------------------------------------------------
+  def refresh_halo(self, x):
+    p = self.part
+    if self.world == 1 or (p.n_halo == 0 and len(p.send_index) == 0):
+      return
+    stream = N.current_stream(self.device)
+    if len(p.send_index):
+      N.check(N.lib().grand_pack_rows(x.data_ptr(), self.send_index.data_ptr(), len(p.send_index), self.d,
+                                      self.send_buf.data_ptr(), stream))
+    exchange_halo(self.send_buf[:len(p.send_index)], x[p.n_own:], p.send_counts, p.recv_counts, self.group)
+
+  def rhs(self, x, ep):
+    """x: [n_cols, d] buffer whose own rows are current; refreshes the halo rows, then projection + fused edges."""
+    self.refresh_halo(x)
+    lib, stream = N.lib(), N.current_stream(self.device)
+    g, a = C.byref(self.plan.struct()), C.byref(self.spec.struct)
+    N.check(lib.grand_project_qk(x.data_ptr(), self.part.n_own, self.part.n_cols, a, self.ws.q, self.ws.k, stream))
+    N.check(lib.grand_rhs_attention_edges(g, a, x.data_ptr(), C.byref(self.ws), C.byref(ep), stream))
+
+  def epilogue(self, x0, **outputs):
+    f = self.func
+    return RhsEngine.epilogue(f.alpha_train.detach(), f.beta_train.detach(), x0 if f.opt['add_source'] else None,
+                              f.opt['no_alpha_sigmoid'], **outputs)
+
+  # ---- fixed-grid rk4 (3/8 rule), euler, midpoint: same stage algebra as grand_integrate_fixed ---------------
+  def integrate_fixed(self, y, x0, method, dts):
+    """y: [n_cols, d] buffer, own rows = y(t0); returns the buffer holding y(t_end) (own rows)."""
+    yb, yc, k1, k2, k3 = (self.buffer(n) for n in ('yb', 'yc', 'k1', 'k2', 'k3'))
+    cur, nxt = y, yc
+    per_step = {'euler': 1, 'midpoint': 2, 'rk4': 4}[method]
+    for h in dts:
+      self.func._bump_nfe(per_step)
+      if method == 'euler':
+        self.rhs(cur, self.epilogue(x0, y_out=nxt, coef_f=h, terms=[(cur, 1.0)]))
+      elif method == 'midpoint':
+        self.rhs(cur, self.epilogue(x0, y_out=yb, coef_f=0.5 * h, terms=[(cur, 1.0)]))
+        self.rhs(yb, self.epilogue(x0, y_out=nxt, coef_f=h, terms=[(cur, 1.0)]))
+      else:
+        third = 1.0 / 3.0
+        self.rhs(cur, self.epilogue(x0, f_out=k1, y_out=yb, coef_f=h * third, terms=[(cur, 1.0)]))
+        self.rhs(yb, self.epilogue(x0, f_out=k2, y_out=nxt, coef_f=h, terms=[(cur, 1.0), (k1, -h * third)]))
+        self.rhs(nxt, self.epilogue(x0, f_out=k3, y_out=yb, coef_f=h, terms=[(cur, 1.0), (k1, h), (k2, -h)]))
+        self.rhs(yb, self.epilogue(x0, y_out=nxt, coef_f=h * 0.125,
+                                   terms=[(cur, 1.0), (k1, h * 0.125), (k2, 3 * h * 0.125), (k3, 3 * h * 0.125)]))
+      cur, nxt = nxt, cur
+    return cur
+
+  def forward_block(self, x_own, x0_own, opt, use_graph=False):
+    """Block forward over [0, T] for this rank's rows: returns z for the own rows."""
+    dts, _ = fixed_grid_dts(0.0, opt['time'], opt['step_size'])
+    y = self.buffer('y')
+    self.own(y).copy_(x_own)
+    x0 = self.buffer('x0')
+    self.own(x0).copy_(x0_own)
+    out = self.integrate_fixed(y, x0, opt['method'], dts)
+    return self.own(out)

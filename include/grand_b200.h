@@ -184,6 +184,10 @@ int grand_integrate_fixed(const grand_graph* g, const grand_attention* a, const 
                           const grand_workspace* ws, const grand_epilogue* residual, int32_t method,
                           const float* dt, int32_t n_steps, float* y, float* stage_buffers, void* stream);
 
+/* out[r, :] = x[idx[r], :] for r < n_idx: packs the boundary rows other shards need into a contiguous send buffer
+ * (node-partitioned multi-GPU halo exchange; new design, the reference has no distributed path). */
+int grand_pack_rows(const float* x, const int32_t* idx, int64_t n_idx, int32_t d, float* out, void* stream);
+
 /* y_out = sum_t coef[t] * term[t]  (n elements); the dense-output / interpolation arithmetic of the solvers. */
 int grand_lincomb(int64_t n, int32_t n_terms, const float* const* term, const float* coef, float* y_out,
                   void* stream);
