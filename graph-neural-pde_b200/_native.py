@@ -28,7 +28,7 @@ class GrandGraph(C.Structure):
   _fields_ = [('n_rows', C.c_int32), ('n_cols', C.c_int32), ('n_edges', C.c_int32), ('n_tiles', C.c_int32),
               ('n_split_rows', C.c_int32), ('n_split_tiles', C.c_int32),
               ('rowptr', C.c_void_p), ('col', C.c_void_p), ('erow', C.c_void_p), ('eid', C.c_void_p),
-              ('tile_row', C.c_void_p), ('tile_beg', C.c_void_p), ('tile_nrows', C.c_void_p), ('tile_split', C.c_void_p),
+              ('win_hdr', C.c_void_p), ('win_rec', C.c_void_p),
               ('split_tile0', C.c_void_p), ('colptr', C.c_void_p), ('csc_pos', C.c_void_p)]
 
 
@@ -48,7 +48,7 @@ class GrandEpilogue(C.Structure):
 
 class GrandWorkspace(C.Structure):
   _fields_ = [('q', C.c_void_p), ('k', C.c_void_p), ('scores', C.c_void_p), ('seg_stats', C.c_void_p),
-              ('split_stats', C.c_void_p), ('split_partial', C.c_void_p), ('split_counter', C.c_void_p),
+              ('split_stats', C.c_void_p), ('row_stats', C.c_void_p), ('split_partial', C.c_void_p), ('split_counter', C.c_void_p),
               ('gmax', C.c_void_p)]
 
 

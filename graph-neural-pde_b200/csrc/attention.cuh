@@ -15,6 +15,7 @@ struct AttnView {
   int norm_type;
   int norm_idx;
   float sqrt_dk;                  // (float)np.sqrt(d_k): the reference divides by it (:196)
+  float inv_sqrt_dk_exact;        // 1/sqrt(d_k) when that is an exact power of two, else 0
   const float* kernel_scalars;    // device [4]
   const float* edge_weight_csr;   // or null
 };

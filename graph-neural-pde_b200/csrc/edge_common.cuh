@@ -1,0 +1,149 @@
+// Views, PTX wrappers and warp helpers shared by the edge-phase translation units.
+#pragma once
+#include "attention.cuh"
+
+namespace grand {
+
+constexpr int MODE_FUSED = 0;     // scaled_dot scores + row softmax computed in the kernel
+constexpr int MODE_PRECOMP = 1;   // scores / segment statistics from the general pre-pass
+constexpr int MODE_WEIGHT = 2;    // GRAND-l: per-edge weights given
+
+constexpr int STAGE_DIRECT = 0;   // neighbour rows straight into registers, a batch at a time
+constexpr int STAGE_CPASYNC = 1;  // cp.async (LDGSTS) into the warp's shared-memory window buffer
+constexpr int STAGE_BULK = 2;     // cp.async.bulk (TMA bulk copy) + mbarrier into the window buffer
+
+// window header written by the host plan (graph_plan.py): one int4 per window
+//   .x first (or only) row   .y first CSR position   .z nrows | cnt << 8   .w split-row index or -1
+// per-lane record: one int2 per lane
+//   .x column j of the lane's edge (0 for idle lanes)
+//   .y bits 0-7 row index inside the window, 8-13 segment lo, 14-19 segment hi (lanes of the lane's own row),
+//      bits 20-25 / 26-31: lo / hi of row number `lane` (valid for lane < nrows)
+struct GraphView {
+  int n_rows, n_cols, n_edges, n_tiles, n_split_rows, n_split_tiles;
+  const int *rowptr, *col, *erow, *eid, *split_tile0, *colptr, *csc_pos;
+  const int4* win_hdr;
+  const int2* win_rec;
+};
+
+struct EpiView {
+  const float* alpha_train;
+  const float* beta_train;
+  const float* x0;
+  int no_alpha_sigmoid;
+  int n_terms;
+  float* f_out;
+  float* y_out;
+  float coef_f;
+  float coef[GRAND_MAX_TERMS];
+  const float* term[GRAND_MAX_TERMS];
+};
+
+struct RhsArgs {
+  GraphView g;
+  AttnView a;          // MODE_FUSED / MODE_PRECOMP
+  EpiView ep;
+  int d;
+  const float* x;      // [n_cols, d]
+  const float* q;      // [n_rows, ad_eff]
+  const float* k;      // [n_cols, ad_eff]
+  const float* w_csr;  // MODE_WEIGHT
+  const float* scores;       // MODE_PRECOMP [E, H]
+  const float* seg_stats;    // MODE_PRECOMP [n_seg, H, 2]
+  const float* gmax;         // squareplus global max
+  float* split_stats;        // [n_split_tiles, H, 2] per-chunk (max, sum-exp)
+  float* row_stats;          // [n_split_rows, H, 2] merged per long row
+  float* split_partial;      // [n_split_tiles, d]
+  int* split_counter;        // [n_split_rows]
+};
+
+// ---- shared-memory async copies and mbarrier -----------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const float* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_copy_g2s(uint32_t dst, const float* src, uint32_t bytes, uint32_t bar,
+                                              uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::
+          "r"(dst),
+      "l"(src), "r"(bytes), "r"(bar), "l"(policy)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+
+// ---- L2 residency: the gather sources (X, K, Q: ~108 MB on ogbn-arxiv) should stay in the 126 MB L2 across the
+//      launch, the streamed stage buffers should not push them out --------------------------------------------
+__device__ __forceinline__ uint64_t policy_evict_last() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ uint64_t policy_evict_first() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ float4 ldg4_hint(const float* p, uint64_t policy) {
+  float4 r;
+  asm volatile("ld.global.nc.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+               : "l"(p), "l"(policy));
+  return r;
+}
+__device__ __forceinline__ float4 ld_stream4_hint(const float* p, uint64_t policy) {
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+               : "l"(p), "l"(policy));
+  return r;
+}
+__device__ __forceinline__ void st_stream4_hint(float* p, float4 v, uint64_t policy) {
+  asm volatile("st.global.L1::no_allocate.L2::cache_hint.v4.f32 [%0], {%1,%2,%3,%4}, %5;" ::"l"(p), "f"(v.x),
+               "f"(v.y), "f"(v.z), "f"(v.w), "l"(policy)
+               : "memory");
+}
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+// ---- segmented all-reduce over contiguous lane segments [lo, hi): every lane gets its own segment's value ----
+__device__ __forceinline__ float seg_max(float v, int lane, int lo, int hi) {
+#pragma unroll
+  for (int o = 1; o < kWarp; o <<= 1) {
+    const float t = __shfl_down_sync(kFull, v, o);
+    if (lane + o < hi) v = fmaxf(v, t);
+  }
+  return __shfl_sync(kFull, v, lo);
+}
+__device__ __forceinline__ float seg_sum(float v, int lane, int lo, int hi) {
+#pragma unroll
+  for (int o = 1; o < kWarp; o <<= 1) {
+    const float t = __shfl_down_sync(kFull, v, o);
+    if (lane + o < hi) v += t;
+  }
+  return __shfl_sync(kFull, v, lo);
+}
+
+}  // namespace grand

@@ -98,6 +98,7 @@ class RhsEngine:
     f = lambda n: torch.empty(max(int(n), 1), dtype=torch.float32, device=dev)
     keep = dict(q=f(p.n_rows * ad_eff), k=f(p.n_cols * ad_eff), scores=f(p.n_edges * heads),
                 seg_stats=f(p.n_cols * heads * 2), split_stats=f(p.n_split_tiles * max(heads, 1) * 2),
+                row_stats=f(p.n_split_rows * max(heads, 1) * 2),
                 split_partial=f(p.n_split_tiles * self.d),
                 split_counter=torch.zeros(max(p.n_split_rows, 1), dtype=torch.int32, device=dev), gmax=f(1))
     ws = N.GrandWorkspace()

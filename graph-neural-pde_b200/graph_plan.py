@@ -94,6 +94,34 @@ class GraphPlan:
     tile_split = torch.cat([st_split, torch.full_like(pack_row, -1)])
 
     col_csr = col[perm]
+    # window header (int4) and per-lane record (int2), see csrc/edge_common.cuh
+    n_t = int(tile_row.numel())
+    is_split = tile_split >= 0
+    t_end = torch.where(is_split, torch.minimum(tile_beg + tile, rowptr[tile_row + 1]), rowptr[tile_row + tile_nrows])
+    t_cnt = t_end - tile_beg
+    win_hdr = torch.stack([tile_row, tile_beg, tile_nrows | (t_cnt << 8), tile_split], dim=1)
+    lane = torch.arange(tile, device=device).unsqueeze(0)                       # [1, 32]
+    pos = tile_beg.unsqueeze(1) + lane                                         # CSR position of every lane
+    lane_valid = lane < t_cnt.unsqueeze(1)
+    pos_c = torch.where(lane_valid, pos, torch.zeros_like(pos)).clamp(max=max(e - 1, 0))
+    lane_col = torch.where(lane_valid, col_csr[pos_c] if e > 0 else torch.zeros_like(pos), torch.zeros_like(pos))
+    lane_row = (row[perm][pos_c] if e > 0 else torch.zeros_like(pos))
+    kk = torch.where(lane_valid & ~is_split.unsqueeze(1), lane_row - tile_row.unsqueeze(1), torch.zeros_like(pos))
+    # lane range of the lane's own row inside the window
+    own_row = tile_row.unsqueeze(1) + kk
+    seg_lo = torch.where(is_split.unsqueeze(1), torch.zeros_like(pos), rowptr[own_row] - tile_beg.unsqueeze(1))
+    seg_hi = torch.where(is_split.unsqueeze(1), t_cnt.unsqueeze(1).expand_as(pos), rowptr[own_row + 1] - tile_beg.unsqueeze(1))
+    seg_lo = torch.where(lane_valid, seg_lo, lane.expand_as(pos))
+    seg_hi = torch.where(lane_valid, seg_hi, lane.expand_as(pos))
+    # lane range of row number `lane` of the window (lane < nrows)
+    has_row = lane < tile_nrows.unsqueeze(1)
+    rrow = (tile_row.unsqueeze(1) + lane).clamp(max=max(n_rows - 1, 0))
+    row_lo = torch.where(has_row & ~is_split.unsqueeze(1), rowptr[rrow] - tile_beg.unsqueeze(1), torch.zeros_like(pos))
+    row_hi = torch.where(has_row & ~is_split.unsqueeze(1), rowptr[rrow + 1] - tile_beg.unsqueeze(1), torch.zeros_like(pos))
+    packed = kk | (seg_lo << 8) | (seg_hi << 14) | (row_lo << 20) | (row_hi << 26)
+    packed = torch.where(packed >= 2 ** 31, packed - 2 ** 32, packed)           # two's complement into int32
+    win_rec = torch.stack([lane_col, packed], dim=2)                            # [n_tiles, 32, 2]
+    assert n_t == 0 or (int(t_cnt.max()) <= tile and int(t_cnt.min()) >= 0)
     perm_c = torch.argsort(col_csr, stable=True)
     cdeg = torch.bincount(col, minlength=n_cols)
     colptr = torch.zeros(n_cols + 1, dtype=torch.long, device=device)
@@ -109,6 +137,7 @@ class GraphPlan:
     self.rowptr, self.col, self.erow, self.eid = i32(rowptr), i32(col_csr), i32(row[perm]), i32(perm)
     self.tile_row, self.tile_beg, self.tile_split = i32(tile_row), i32(tile_beg), i32(tile_split)
     self.tile_nrows = i32(tile_nrows)
+    self.win_hdr, self.win_rec = i32(win_hdr), i32(win_rec)
     self.split_tile0 = i32(split_tile0)
     self.colptr, self.csc_pos = i32(colptr), i32(perm_c)
     self.eid_long = perm  # CSR position -> caller position (int64, for torch-side permutations)
@@ -120,8 +149,7 @@ class GraphPlan:
       g = N.GrandGraph()
       g.n_rows, g.n_cols, g.n_edges, g.n_tiles = self.n_rows, self.n_cols, self.n_edges, self.n_tiles
       g.n_split_rows, g.n_split_tiles = self.n_split_rows, self.n_split_tiles
-      for name in ('rowptr', 'col', 'erow', 'eid', 'tile_row', 'tile_beg', 'tile_nrows', 'tile_split', 'split_tile0',
-                   'colptr', 'csc_pos'):
+      for name in ('rowptr', 'col', 'erow', 'eid', 'win_hdr', 'win_rec', 'split_tile0', 'colptr', 'csc_pos'):
         setattr(g, name, getattr(self, name).data_ptr())
       self._struct = g
     return self._struct

@@ -71,10 +71,10 @@ typedef struct grand_graph {
   const int32_t* col;          /* [n_edges] edge_index[1] in CSR order                                */
   const int32_t* erow;         /* [n_edges] edge_index[0] in CSR order                                */
   const int32_t* eid;          /* [n_edges] CSR position -> position in the caller's edge list        */
-  const int32_t* tile_row;     /* [n_tiles] first (or only) row of the tile                           */
-  const int32_t* tile_beg;     /* [n_tiles] first CSR position of the tile                            */
-  const int32_t* tile_nrows;   /* [n_tiles] whole rows packed into the tile (1 for a chunk of a long row) */
-  const int32_t* tile_split;   /* [n_tiles] -1, else index of the split row the tile belongs to       */
+  const int32_t* win_hdr;      /* [n_tiles, 4] per window: first row, first CSR position, nrows | cnt << 8,
+                                  split-row index or -1                                                */
+  const int32_t* win_rec;      /* [n_tiles, 32, 2] per lane: column; row-in-window | lo << 8 | hi << 14 |
+                                  row-lane-range (lo << 20 | hi << 26) -- see csrc/edge_common.cuh      */
   const int32_t* split_tile0;  /* [n_split_rows + 1] first split-tile slot of each split row          */
   const int32_t* colptr;       /* [n_cols + 1] CSC by edge_index[1] (may be null if norm_idx 1 unused)*/
   const int32_t* csc_pos;      /* [n_edges] CSC position -> CSR position                              */
@@ -125,7 +125,8 @@ typedef struct grand_workspace {
   float* k;                    /* [n_cols, ad_eff]                                                    */
   float* scores;               /* [n_edges, heads]   general path only                                */
   float* seg_stats;            /* [n_cols, heads, 2] general path only: (max, sum) per segment        */
-  float* split_stats;          /* [n_split_tiles, heads, 2]                                           */
+  float* split_stats;          /* [n_split_tiles, heads, 2] per chunk of a long row: (max, sum-exp)   */
+  float* row_stats;            /* [n_split_rows, heads, 2] the same merged per long row               */
   float* split_partial;        /* [n_split_tiles, d]                                                  */
   int32_t* split_counter;      /* [n_split_rows], zero on first use; kernels leave it zero            */
   float* gmax;                 /* [1] global max for squareplus (ordered-int encoded during reduction)*/
