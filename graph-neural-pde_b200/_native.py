@@ -9,7 +9,7 @@ import os
 import torch
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, 'libgrand_b200.so')
+LIB_PATH = os.environ.get('GRAND_LIB') or os.path.join(HERE, 'libgrand_b200.so')   # GRAND_LIB: A/B builds
 
 GRAND_TILE = 32
 GRAND_MAX_HEADS = 8

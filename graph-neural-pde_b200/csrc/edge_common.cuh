@@ -54,6 +54,7 @@ struct RhsArgs {
   float* row_stats;          // [n_split_rows, H, 2] merged per long row
   float* split_partial;      // [n_split_tiles, d]
   int* split_counter;        // [n_split_rows]
+  int l2_hints;              // bit 0: evict_last on the gathers, bit 1: evict_first on the streams
 };
 
 // ---- shared-memory async copies and mbarrier -----------------------------------------------------------------
@@ -105,6 +106,11 @@ __device__ __forceinline__ uint64_t policy_evict_last() {
 __device__ __forceinline__ uint64_t policy_evict_first() {
   uint64_t p;
   asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ uint64_t policy_evict_normal() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(p));
   return p;
 }
 __device__ __forceinline__ float4 ldg4_hint(const float* p, uint64_t policy) {

@@ -193,6 +193,16 @@ static int check_graph(const grand_graph* g) {
 }
 
 int launch_rhs_mode(int mode, const RhsArgs& A, cudaStream_t stream);
+
+// GRAND_L2_HINTS=0..3 (bit 0 evict_last gathers, bit 1 evict_first streams); default from round-1 measurements
+static int l2_hints() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("GRAND_L2_HINTS");
+    v = e != nullptr ? atoi(e) & 3 : 3;
+  }
+  return v;
+}
 int launch_split_stats(const RhsArgs& A, cudaStream_t stream);
 
 int launch_project_qk(const float* x, int n_rows, int n_cols, int d, const float* wq, const float* bq,
@@ -242,6 +252,7 @@ int rhs_attention_impl(const grand_graph* g, const grand_attention* a, const flo
   A.d = a->d;
   A.x = x; A.q = ws->q; A.k = ws->k; A.w_csr = nullptr;
   A.scores = ws->scores; A.seg_stats = ws->seg_stats; A.gmax = ws->gmax;
+  A.l2_hints = l2_hints();
   A.split_stats = ws->split_stats; A.row_stats = ws->row_stats; A.split_partial = ws->split_partial;
   A.split_counter = ws->split_counter;
   GRAND_REQUIRE(g->n_split_tiles == 0 || (ws->split_partial && ws->split_counter), GRAND_EINVAL,
@@ -279,6 +290,7 @@ int rhs_laplacian_impl(const grand_graph* g, int d, const float* x, const float*
   A.d = d;
   A.x = x; A.q = nullptr; A.k = nullptr; A.w_csr = w_csr;
   A.scores = nullptr; A.seg_stats = nullptr; A.gmax = nullptr; A.split_stats = nullptr; A.row_stats = nullptr;
+  A.l2_hints = l2_hints();
   A.split_partial = ws ? ws->split_partial : nullptr;
   A.split_counter = ws ? ws->split_counter : nullptr;
   return launch_rhs_mode(MODE_WEIGHT, A, stream);

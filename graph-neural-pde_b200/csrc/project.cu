@@ -22,6 +22,7 @@ project_qk_kernel(const float* __restrict__ x, int n_rows, int n_cols, int d, in
   float* ws = smem;                       // [out][ld]
   float* xs = smem + (size_t)out * ld;    // [rows_per_tile][ld]
   const int tid = threadIdx.x;
+  const int nthreads = blockDim.x;   // 128 or 256
   const int c4n = d4 >> 2;
 
   // stage the weights once per CTA (zero padded to d4); loads are batched ahead of the shared stores so that a CTA
@@ -29,11 +30,11 @@ project_qk_kernel(const float* __restrict__ x, int n_rows, int n_cols, int d, in
   if ((d & 3) == 0) {
     const int total = out * c4n;
     constexpr int kBatch = 8;
-    for (int base = tid; base < total; base += kProjThreads * kBatch) {
+    for (int base = tid; base < total; base += nthreads * kBatch) {
       float4 v[kBatch];
 #pragma unroll
       for (int u = 0; u < kBatch; ++u) {
-        const int idx = base + u * kProjThreads;
+        const int idx = base + u * nthreads;
         v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (idx < total) {
           const int o = idx / c4n, c4 = idx - o * c4n;
@@ -43,7 +44,7 @@ project_qk_kernel(const float* __restrict__ x, int n_rows, int n_cols, int d, in
       }
 #pragma unroll
       for (int u = 0; u < kBatch; ++u) {
-        const int idx = base + u * kProjThreads;
+        const int idx = base + u * nthreads;
         if (idx < total) {
           const int o = idx / c4n, c4 = idx - o * c4n;
           *reinterpret_cast<float4*>(ws + o * ld + 4 * c4) = v[u];
@@ -51,7 +52,7 @@ project_qk_kernel(const float* __restrict__ x, int n_rows, int n_cols, int d, in
       }
     }
   } else {
-    for (int idx = tid; idx < out * d4; idx += kProjThreads) {
+    for (int idx = tid; idx < out * d4; idx += nthreads) {
       const int o = idx / d4, c = idx - o * d4;
       float v = 0.f;
       if (c < d) v = (o < ad) ? wq[(size_t)o * d + c] : wk[(size_t)(o - ad) * d + c];
@@ -69,14 +70,14 @@ project_qk_kernel(const float* __restrict__ x, int n_rows, int n_cols, int d, in
     const int row0 = tile * rows_per_tile;
     __syncthreads();  // previous tile's compute is done (and the weights are visible on the first pass)
     if (vec_ok) {
-      for (int idx = tid; idx < rows_per_tile * c4n; idx += kProjThreads) {
+      for (int idx = tid; idx < rows_per_tile * c4n; idx += nthreads) {
         const int r = idx / c4n, c4 = idx - r * c4n;
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         if (row0 + r < n_cols) v = ld_stream4(x + (size_t)(row0 + r) * d + 4 * c4);
         *reinterpret_cast<float4*>(xs + r * ld + 4 * c4) = v;
       }
     } else {
-      for (int idx = tid; idx < rows_per_tile * d4; idx += kProjThreads) {
+      for (int idx = tid; idx < rows_per_tile * d4; idx += nthreads) {
         const int r = idx / d4, c = idx - r * d4;
         float v = 0.f;
         if (row0 + r < n_cols && c < d) v = x[(size_t)(row0 + r) * d + c];
@@ -142,7 +143,10 @@ int launch_project_qk(const float* x, int n_rows, int n_cols, int d, const float
                 kProjThreads * OT / 2);
   const int d4 = (d + 3) & ~3;
   const int ld = ((d4 >> 2) & 1) ? d4 : d4 + 4;  // ld/4 odd -> conflict-free 128-bit shared loads across rows
-  const int ty_count = kProjThreads / tx_count;
+  // narrow outputs (few thread columns): 128-thread CTAs with small row tiles, so that several CTAs per SM overlap one
+  // CTA's tile load with another's arithmetic; wide outputs keep 256 threads
+  const int threads = tx_count <= 16 ? 128 : kProjThreads;
+  const int ty_count = threads / tx_count;
   const int rows_per_tile = ty_count * RT;
   const int n_tiles = (n_cols + rows_per_tile - 1) / rows_per_tile;
   const size_t smem = (size_t)(out + rows_per_tile) * ld * sizeof(float);
@@ -156,10 +160,10 @@ int launch_project_qk(const float* x, int n_rows, int n_cols, int d, const float
   }
   int per_sm = (int)((227 * 1024) / (smem + 1024));
   if (per_sm < 1) per_sm = 1;
-  if (per_sm > 4) per_sm = 4;
+  if (per_sm > 6) per_sm = 6;
   int grid = num_sms() * per_sm;
   if (grid > n_tiles) grid = n_tiles;
-  kern<<<grid, kProjThreads, smem, stream>>>(x, n_rows, n_cols, d, d4, ld, wq, bq, wk, bk, ad, tx_count,
+  kern<<<grid, threads, smem, stream>>>(x, n_rows, n_cols, d, d4, ld, wq, bq, wk, bk, ad, tx_count,
                                              rows_per_tile, n_tiles, q, k);
   GRAND_CUDA_OK(cudaGetLastError());
   count_launch();

@@ -25,7 +25,13 @@ namespace grand {
 
 constexpr int kRhsThreads = 128;  // 4 warps per block
 constexpr int kRhsWarps = kRhsThreads / kWarp;
-constexpr int kDirectBatch = 8;   // STAGE_DIRECT: neighbour rows in flight per warp (divided by R)
+#ifndef GRAND_DIRECT_BATCH
+#define GRAND_DIRECT_BATCH 8
+#endif
+#ifndef GRAND_DIRECT_MINBLOCKS
+#define GRAND_DIRECT_MINBLOCKS 8
+#endif
+constexpr int kDirectBatch = GRAND_DIRECT_BATCH;   // STAGE_DIRECT: neighbour rows in flight per warp (divided by R)
 
 // q.k over one head, then the reference's division by np.sqrt(d_k) (:196); for d_k a power of 4 the division is an
 // exact power-of-two scaling and is done as a multiplication (bit-identical).
@@ -150,9 +156,40 @@ __device__ __forceinline__ void finish_row(const RhsArgs& A, int row, int lane, 
   }
 }
 
+// ---- STAGE_DIRECT: NB neighbour rows of one query row in flight in registers, then accumulated ----------------------
+template <int VEC, int R, int NB>
+__device__ __forceinline__ void gather_batch(const float* __restrict__ xl, int d, int lane, bool full, int j, float ab,
+                                             int e, uint64_t pol_keep, float (&acc)[R][VEC]) {
+  float aa[NB];
+  float xv[NB][R][VEC];
+#pragma unroll
+  for (int u = 0; u < NB; ++u) {
+    const int ju = __shfl_sync(kFull, j, e + u);
+    aa[u] = __shfl_sync(kFull, ab, e + u);
+    const float* xr = xl + (size_t)ju * d;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const int c = (lane + r * kWarp) * VEC;
+      if (VEC == 4) {
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (full || c < d) v = ldg4_hint(xr + r * kWarp * VEC, pol_keep);
+        xv[u][r][0] = v.x; xv[u][r][1 % VEC] = v.y; xv[u][r][2 % VEC] = v.z; xv[u][r][3 % VEC] = v.w;
+      } else {
+        xv[u][r][0] = c < d ? __ldg(xr + r * kWarp) : 0.f;
+      }
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < NB; ++u)
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) acc[r][v] = fmaf(aa[u], xv[u][r][v], acc[r][v]);
+}
+
 // ---- the RHS kernel -----------------------------------------------------------------------------------------------------
 template <int MODE, int VEC, int R, int STAGE>
-__global__ void __launch_bounds__(kRhsThreads, STAGE == STAGE_DIRECT ? 5 : 3)
+__global__ void __launch_bounds__(kRhsThreads, STAGE == STAGE_DIRECT ? GRAND_DIRECT_MINBLOCKS : 3)
 rhs_window_kernel(const __grid_constant__ RhsArgs A) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31;
@@ -170,8 +207,8 @@ rhs_window_kernel(const __grid_constant__ RhsArgs A) {
   const int kk = rec.y & 0xff, lo = (rec.y >> 8) & 0x3f, hi = (rec.y >> 14) & 0x3f;
   const bool valid = lane < cnt;
   const int i = row0 + kk;
-  const uint64_t pol_keep = policy_evict_last();
-  const uint64_t pol_stream = policy_evict_first();
+  const uint64_t pol_keep = (A.l2_hints & 1) ? policy_evict_last() : policy_evict_normal();
+  const uint64_t pol_stream = (A.l2_hints & 2) ? policy_evict_first() : policy_evict_normal();
 
   // ---- level 2a: start moving every neighbour row of the window --------------------------------------------------
   float* stage = nullptr;
@@ -309,40 +346,15 @@ rhs_window_kernel(const __grid_constant__ RhsArgs A) {
         }
       }
     } else {
+      // exact decomposition of the row's edge count into batches of U, U/2, ..., 1 rows in flight: no padded loads
       constexpr int U = (kDirectBatch / R) < 2 ? 2 : (kDirectBatch / R);
-      for (int e0 = e_lo; e0 < e_hi; e0 += U) {
-        int jj[U];
-        float aa[U];
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-          const int src = min(e0 + u, e_hi - 1);
-          jj[u] = __shfl_sync(kFull, j, src);
-          aa[u] = __shfl_sync(kFull, ab, src);
-          if (e0 + u >= e_hi) aa[u] = 0.f;
-        }
-        float xv[U][R][VEC];
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-          const float* xr = A.x + (size_t)jj[u] * d;
-#pragma unroll
-          for (int r = 0; r < R; ++r) {
-            const int c = (lane + r * kWarp) * VEC;
-            if (VEC == 4) {
-              float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-              if (full || c < d) v = ldg4_hint(xr + c, pol_keep);
-              xv[u][r][0] = v.x; xv[u][r][1 % VEC] = v.y; xv[u][r][2 % VEC] = v.z; xv[u][r][3 % VEC] = v.w;
-            } else {
-              xv[u][r][0] = c < d ? __ldg(xr + c) : 0.f;
-            }
-          }
-        }
-#pragma unroll
-        for (int u = 0; u < U; ++u)
-#pragma unroll
-          for (int r = 0; r < R; ++r)
-#pragma unroll
-            for (int v = 0; v < VEC; ++v) acc[r][v] = fmaf(aa[u], xv[u][r][v], acc[r][v]);
-      }
+      const float* xl = A.x + (size_t)lane * VEC;
+      int e = e_lo;
+      while (e_hi - e >= U) { gather_batch<VEC, R, U>(xl, d, lane, full, j, ab, e, pol_keep, acc); e += U; }
+      if (U >= 8 && e_hi - e >= 4) { gather_batch<VEC, R, 4>(xl, d, lane, full, j, ab, e, pol_keep, acc); e += 4; }
+      if (U >= 4 && e_hi - e >= 2) { gather_batch<VEC, R, 2>(xl, d, lane, full, j, ab, e, pol_keep, acc); e += 2; }
+      if (e_hi - e >= 1) { gather_batch<VEC, R, 1>(xl, d, lane, full, j, ab, e, pol_keep, acc); e += 1; }
+      if (U == 2 && e_hi - e >= 1) gather_batch<VEC, R, 1>(xl, d, lane, full, j, ab, e, pol_keep, acc);
     }
 
     if (split < 0) {
