@@ -33,6 +33,9 @@ int rhs_laplacian_impl(const grand_graph* g, int d, const float* x, const float*
 int attention_weights_impl(const grand_graph* g, const grand_attention* a, const float* x, const grand_workspace* ws,
                            float* attention_out, float* prods_out, float* mean_csr_out, cudaStream_t stream);
 int edge_values_to_csr_impl(const grand_graph* g, const float* w, int heads, float* w_csr, cudaStream_t stream);
+int rhs_attention_backward_host(const grand_graph* g, const grand_attention* a, const float* x, const float* grad_f,
+                                const grand_workspace* ws, const float* alpha_train, int no_alpha_sigmoid,
+                                float* row_dot, float* abar_out, float* dq, float* dk, cudaStream_t stream);
 
 // ---------------------------------------------------------------------------------------------------------
 // dense helpers
@@ -154,6 +157,14 @@ int grand_rhs_attention(const grand_graph* g, const grand_attention* a, const fl
 int grand_rhs_attention_edges(const grand_graph* g, const grand_attention* a, const float* x, const grand_workspace* ws,
                               const grand_epilogue* ep, void* stream) {
   return rhs_attention_impl(g, a, x, ws, ep, false, (cudaStream_t)stream);
+}
+
+int grand_rhs_attention_backward(const grand_graph* g, const grand_attention* a, const float* x, const float* grad_f,
+                                 const grand_workspace* ws, const float* alpha_train, int32_t no_alpha_sigmoid,
+                                 float* row_dot, float* abar_out, float* dq, float* dk, void* stream) {
+  GRAND_REQUIRE(a && a->wq && a->bq && a->wk && a->bk, GRAND_EINVAL, "rhs_attention_backward: null attention weights");
+  return rhs_attention_backward_host(g, a, x, grad_f, ws, alpha_train, no_alpha_sigmoid, row_dot, abar_out, dq, dk,
+                                     (cudaStream_t)stream);
 }
 
 int grand_rhs_laplacian(const grand_graph* g, int32_t d, const float* x, const float* w_csr, const grand_workspace* ws,

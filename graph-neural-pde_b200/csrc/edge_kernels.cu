@@ -274,6 +274,37 @@ int rhs_attention_impl(const grand_graph* g, const grand_attention* a, const flo
   return launch_rhs_mode(MODE_PRECOMP, A, stream);
 }
 
+int rhs_attention_backward_impl(const grand_graph* g, const grand_attention* a, const float* x, const float* grad_f,
+                                const grand_workspace* ws, const float* alpha_train, int no_alpha_sigmoid,
+                                float* row_dot, float* abar_out, float* dq, float* dk, GraphView gv,
+                                cudaStream_t stream);
+
+int rhs_attention_backward_host(const grand_graph* g, const grand_attention* a, const float* x, const float* grad_f,
+                                const grand_workspace* ws, const float* alpha_train, int no_alpha_sigmoid,
+                                float* row_dot, float* abar_out, float* dq, float* dk, cudaStream_t stream) {
+  int rc;
+  if ((rc = check_graph(g)) != GRAND_OK) return rc;
+  GRAND_REQUIRE(a && x && grad_f && ws && ws->q && ws->k && alpha_train && abar_out && dq && dk, GRAND_EINVAL,
+                "rhs_attention_backward: null argument");
+  GRAND_REQUIRE(g->n_cols == g->n_rows, GRAND_EUNSUPPORTED, "rhs_attention_backward: sharded graphs are not built");
+  RhsArgs A;
+  A.g = view(g);
+  if ((rc = make_attn_view(a, &A.a)) != GRAND_OK) return rc;
+  A.d = a->d;
+  A.x = x; A.q = ws->q; A.k = ws->k;
+  A.split_stats = ws->split_stats; A.row_stats = ws->row_stats; A.split_partial = ws->split_partial;
+  A.split_counter = ws->split_counter;
+  rc = launch_project_qk(x, g->n_rows, g->n_cols, a->d, a->wq, a->bq, a->wk, a->bk, A.a.ad_eff, ws->q, ws->k, stream);
+  if (rc != GRAND_OK) return rc;
+  if (g->n_split_tiles > 0) {
+    GRAND_REQUIRE(ws->split_stats && ws->row_stats && ws->split_counter, GRAND_EINVAL,
+                  "rhs_attention_backward: graph has long rows, workspace split arrays are null");
+    if ((rc = launch_split_stats(A, stream)) != GRAND_OK) return rc;
+  }
+  return rhs_attention_backward_impl(g, a, x, grad_f, ws, alpha_train, no_alpha_sigmoid, row_dot, abar_out, dq, dk,
+                                     A.g, stream);
+}
+
 int rhs_laplacian_impl(const grand_graph* g, int d, const float* x, const float* w_csr, const grand_workspace* ws,
                        const grand_epilogue* ep, cudaStream_t stream) {
   int rc;

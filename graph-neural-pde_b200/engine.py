@@ -167,6 +167,22 @@ class RhsEngine:
                                             N.current_stream(self.device)))
     return att, prods, mean_csr
 
+  def attention_backward(self, spec, x, grad_f, alpha_train, no_alpha_sigmoid):
+    """Edge phase of the RHS backward (grand_rhs_attention_backward): -> (abar[E] caller order, dQ, dK)."""
+    self._check_state(x)
+    self._check_state(grad_f, 'grad_f')
+    ws = self.workspace(spec)
+    p, dev = self.plan, self.device
+    abar = torch.empty((p.n_edges,), dtype=torch.float32, device=dev)
+    dq = torch.zeros((p.n_rows, spec.ad_eff), dtype=torch.float32, device=dev)
+    dk = torch.zeros((p.n_cols, spec.ad_eff), dtype=torch.float32, device=dev)
+    row_dot = torch.zeros((max(p.n_split_rows, 1) * spec.heads,), dtype=torch.float32, device=dev)
+    N.check(N.lib().grand_rhs_attention_backward(
+      C.byref(p.struct()), C.byref(spec.struct), x.data_ptr(), grad_f.data_ptr(), C.byref(ws),
+      alpha_train.data_ptr(), 1 if no_alpha_sigmoid else 0, row_dot.data_ptr(), abar.data_ptr(), dq.data_ptr(),
+      dk.data_ptr(), N.current_stream(dev)))
+    return abar, dq, dk
+
   def edge_values_to_csr(self, w):
     N.require_cuda(w, 'edge values')
     w = w.contiguous()

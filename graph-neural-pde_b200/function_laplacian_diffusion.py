@@ -7,6 +7,7 @@ import torch
 from torch import nn
 
 from . import _native as N
+from .autograd_rhs import LaplacianRhsFn, needs_grad
 from .base_classes import ODEFunc
 from .engine import RhsEngine
 
@@ -64,9 +65,12 @@ class LaplacianODEFunc(ODEFunc):
   def forward(self, t, x):  # the t param is needed by the ODE solver.
     self._bump_nfe()
     N.require_cuda(x, 'x')
-    if x.requires_grad and torch.is_grad_enabled():
-      raise NotImplementedError('grand_b200: the RHS backward kernels are not built yet (SURVEY.md 8(f).1); '
-                                'call under torch.no_grad()')
+    if needs_grad(self, x):
+      w = self.edge_values()
+      if w is not None and w.requires_grad:
+        raise NotImplementedError('grand_b200 backward: gradients through frozen attention weights (block=attention) '
+                                  'are not built; the constant block trains')
+      return LaplacianRhsFn.apply(x, self.alpha_train, self.beta_train, self)
     x = x.contiguous()
     engine = self.engine(x)
     f = torch.empty_like(x)

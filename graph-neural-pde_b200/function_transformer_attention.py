@@ -10,6 +10,7 @@ import torch
 from torch import nn
 
 from . import _native as N
+from .autograd_rhs import TransformerRhsFn, needs_grad
 from .base_classes import ODEFunc
 from .engine import AttentionSpec, RhsEngine
 from .graph_plan import GraphPlan
@@ -160,9 +161,12 @@ class ODEFuncTransformerAtt(ODEFunc):
                                 'hot path (SURVEY.md 8(f).4)')
     self._bump_nfe()
     N.require_cuda(x, 'x')
-    if x.requires_grad and torch.is_grad_enabled():
-      raise NotImplementedError('grand_b200: the RHS backward kernels are not built yet (SURVEY.md 8(f).1); '
-                                'call under torch.no_grad()')
+    if needs_grad(self, x):
+      layer = self.multihead_att_layer
+      if not hasattr(layer, 'Q'):
+        raise NotImplementedError('grand_b200 backward: the beltrami exp_kernel layer is forward-only')
+      return TransformerRhsFn.apply(x, layer.Q.weight, layer.Q.bias, layer.K.weight, layer.K.bias, self.alpha_train,
+                                    self.beta_train, self)
     x = x.contiguous()
     engine = self.engine(x)
     f = torch.empty_like(x)

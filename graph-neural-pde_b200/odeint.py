@@ -18,6 +18,7 @@ import math
 import torch
 
 from . import _native as N
+from . import autograd_rhs as AG
 from .engine import DP_BETA, DP_C_ERROR, DP_C_MID, RhsEngine, _f32, fixed_grid_dts
 
 FIXED_METHODS = ('euler', 'midpoint', 'rk4')
@@ -36,9 +37,6 @@ class NativeProblem:
   def __init__(self, func, y0):
     _require_native(func)
     N.require_cuda(y0, 'y0')
-    if y0.requires_grad and torch.is_grad_enabled():
-      raise NotImplementedError('grand_b200: backward through the integrator is not built yet (SURVEY.md 8(f).1); '
-                                'call under torch.no_grad()')
     self.func = func
     self.engine = func.engine(y0)
     self.spec, self.w_csr = func.native_description(self.engine)
@@ -241,9 +239,7 @@ def integrate_dopri5(func, y0, t, rtol, atol, on_step=None, max_steps=None):
   return out, solver
 
 
-def odeint(func, y0, t, *, rtol=1e-7, atol=1e-9, method=None, options=None, event_fn=None, **adjoint_kwargs):
-  """torchdiffeq.odeint / odeint_adjoint call-compatible (the adjoint_* keywords are accepted; the adjoint backward
-  pass is SURVEY.md 8(f).1 and not built yet, forward results are identical for both)."""
+def _check_call(y0, method, options, event_fn):
   if event_fn is not None:
     raise NotImplementedError('event handling is not used by the reference hot path')
   if not torch.is_tensor(y0):
@@ -253,11 +249,47 @@ def odeint(func, y0, t, *, rtol=1e-7, atol=1e-9, method=None, options=None, even
   if method in FIXED_METHODS:
     if 'step_size' not in options or options['step_size'] is None:
       raise NotImplementedError('fixed-grid solvers need options["step_size"] (every reference call passes it)')
+  elif method != 'dopri5':
+    raise ValueError('Invalid method "{}". Must be one of {}'.format(method, sorted(FIXED_METHODS + ('dopri5',))))
+  return method, options
+
+
+def _native_solution(func, y0, t, method, options, rtol, atol):
+  if method in FIXED_METHODS:
     return integrate_fixed(func, y0, t, method, options['step_size'])
-  if method == 'dopri5':
-    out, _ = integrate_dopri5(func, y0, t, rtol, atol)
-    return out
-  raise ValueError('Invalid method "{}". Must be one of {}'.format(method, sorted(FIXED_METHODS + ('dopri5',))))
+  out, _ = integrate_dopri5(func, y0, t, rtol, atol)
+  return out
 
 
-odeint_adjoint = odeint
+def odeint(func, y0, t, *, rtol=1e-7, atol=1e-9, method=None, options=None, event_fn=None):
+  """torchdiffeq.odeint call-compatible.  No gradients required: the fused engine path.  Gradients required
+  (training with adjoint=False): the same solvers with every RHS evaluation as one autograd node."""
+  method, options = _check_call(y0, method, options, event_fn)
+  _require_native(func)
+  if AG.needs_grad(func, y0):
+    if method in FIXED_METHODS:
+      _, grid = fixed_grid_dts(float(t[0]), float(t[-1]), options['step_size'])
+      return AG.odeint_fixed_autograd(func, y0, t, method, grid)
+    return AG.odeint_dopri5_autograd(func, y0, t, rtol, atol)
+  return _native_solution(func, y0, t, method, options, rtol, atol)
+
+
+def odeint_adjoint(func, y0, t, *, rtol=1e-7, atol=1e-9, method=None, options=None, event_fn=None,
+                   adjoint_rtol=None, adjoint_atol=None, adjoint_method=None, adjoint_options=None,
+                   adjoint_params=None):
+  """torchdiffeq.odeint_adjoint call-compatible: forward on the fused engine without an autograd graph, backward by
+  integrating the adjoint system (reference call site src/block_constant.py:45-55)."""
+  method, options = _check_call(y0, method, options, event_fn)
+  _require_native(func)
+  if not AG.needs_grad(func, y0):
+    return _native_solution(func, y0, t, method, options, rtol, atol)
+  adjoint_method = adjoint_method or method
+  adjoint_options = dict(adjoint_options if adjoint_options is not None else options)
+  params = tuple(p for p in (adjoint_params if adjoint_params is not None else func.parameters()) if p.requires_grad)
+
+  def fwd(y):
+    return _native_solution(func, y, t, method, options, rtol, atol)
+
+  return AG.OdeintAdjointFn.apply(y0, func, t, fwd, adjoint_method, adjoint_options,
+                                  adjoint_rtol if adjoint_rtol is not None else rtol,
+                                  adjoint_atol if adjoint_atol is not None else atol, *params)

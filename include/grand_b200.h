@@ -161,6 +161,16 @@ int grand_rhs_attention(const grand_graph* g, const grand_attention* a, const fl
 int grand_rhs_attention_edges(const grand_graph* g, const grand_attention* a, const float* x, const grand_workspace* ws,
                               const grand_epilogue* ep, void* stream);
 
+/* Vector-Jacobian product of grand_rhs_attention (edge phase) for the fused configuration (scaled_dot, softmax,
+ * attention_norm_idx 0); the reference obtains it from autograd over src/function_transformer_attention.py:38-53.
+ * Given grad_f = dL/df [n_rows, d]:  abar_out[E] (head-mean attention, CALLER edge order -- feed it to the transposed
+ * aggregation alpha (Abar^T g - g) = grand_rhs_laplacian on the flipped graph), dq [n_rows, ad] = dL/dQ and
+ * dk [n_cols, ad] = dL/dK (both must be zero on entry; the dense tails dX += dQ Wq + dK Wk, dWq = dQ^T X ... are plain
+ * GEMMs left to the caller).  row_dot: [n_split_rows, heads] scratch, zero on entry.  Recomputes Q/K into ws. */
+int grand_rhs_attention_backward(const grand_graph* g, const grand_attention* a, const float* x, const float* grad_f,
+                                 const grand_workspace* ws, const float* alpha_train, int32_t no_alpha_sigmoid,
+                                 float* row_dot, float* abar_out, float* dq, float* dk, void* stream);
+
 /* One GRAND-l RHS evaluation: LaplacianODEFunc.forward (reference src/function_laplacian_diffusion.py:38-51);
  * `w_csr` is the per-edge weight sparse_multiply would use (:28-36) in CSR order. */
 int grand_rhs_laplacian(const grand_graph* g, int32_t d, const float* x, const float* w_csr, const grand_workspace* ws,
