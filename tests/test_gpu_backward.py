@@ -21,6 +21,18 @@ DEV = torch.device('cuda:0')
 GTOL = 2e-4
 
 
+def assert_grads_close(got, want, tol, what):
+  """Per-tensor max-normalised comparison, except that a gradient which is identically zero in exact arithmetic
+  (dL/dK.bias: a constant added to every key shifts all scores of a row equally and the softmax cancels it) is only
+  rounding noise on both sides; such tensors are normalised by the largest gradient of the group instead."""
+  scale = max(float(w.detach().abs().max()) for w in want)
+  for g, w, name in zip(got, want, what):
+    assert tuple(g.shape) == tuple(w.shape), name
+    err = float((g.detach().double().cpu() - w.detach().double().cpu()).abs().max())
+    denom = max(float(w.detach().abs().max()), 1e-3 * scale)
+    assert err <= tol * denom, '%s: error %.3e vs tolerance %.1e * %.3e' % (name, err, tol, denom)
+
+
 def _make(function, n, d, ad, heads, method='rk4', adjoint=False, seed=0, **extra):
   edge_index = make_graph(n, 6 * n, max_degree=150, seed=seed)
   torch.manual_seed(seed + 1)
@@ -81,10 +93,9 @@ def test_rhs_vjp_vs_oracle_autograd(function, d, ad, heads):
   fo = _oracle_func(sd, opt, edge_index, n, x.double(), function)(0.0, xo)
   fo.backward(gout.double())
   C.assert_close(f, fo, C.RTOL, 'forward value')
-  C.assert_close(xd.grad, xo.grad, GTOL, 'dL/dx')
   got = dict(block.named_parameters())
-  for name in NAMES[function]:
-    C.assert_close(got[name].grad, sd[name].grad, GTOL, 'dL/d' + name)
+  assert_grads_close([xd.grad] + [got[k].grad for k in NAMES[function]],
+                     [xo.grad] + [sd[k].grad for k in NAMES[function]], GTOL, ['x'] + NAMES[function])
 
 
 @pytest.mark.parametrize('function', ['transformer', 'laplacian'])
@@ -105,10 +116,27 @@ def test_block_backward_vs_oracle_autograd(function, method):
   (zo * w.double()).sum().backward()
   tol = GTOL if method == 'rk4' else 2e-2     # dopri5: different accepted-step sequences (see test_gpu_parity)
   C.assert_close(z, zo, C.RTOL if method == 'rk4' else 5e-3, 'z')
-  C.assert_close(xd.grad, xo.grad, tol, 'dL/dx')
   got = dict(block.named_parameters())
-  for name in NAMES[function]:
-    C.assert_close(got[name].grad, sd[name].grad, tol, 'dL/d' + name)
+  assert_grads_close([xd.grad] + [got[k].grad for k in NAMES[function]],
+                     [xo.grad] + [sd[k].grad for k in NAMES[function]], tol, ['x'] + NAMES[function])
+
+
+def test_run_gnn_trains_end_to_end(capsys):
+  """The reference's entry point (run_GNN.main) on the synthetic Cora stand-in: a few epochs of GRAND-nl with the
+  default early-stopping model; the loss must fall and the attribute chain main() reads must be alive."""
+  from graph_neural_pde_b200 import run_GNN
+  args = run_GNN.build_parser().parse_args(['--dataset', 'Cora', '--function', 'transformer', '--block', 'constant',
+                                            '--method', 'rk4', '--time', '1.0', '--step_size', '0.5', '--epoch', '6',
+                                            '--hidden_dim', '32', '--attention_dim', '16', '--heads', '4', '--lr', '0.02',
+                                            '--input_dropout', '0.0', '--quiet'])
+  torch.manual_seed(0)
+  train_acc, val_acc, test_acc = run_GNN.main(vars(args))
+  out = capsys.readouterr().out
+  losses = [float(line.split('Loss ')[1].split(',')[0]) for line in out.splitlines() if line.startswith('Epoch:')]
+  assert len(losses) == 5 and losses[-1] < losses[0], losses
+  assert 'backward nfe' in out and 0 <= val_acc <= 1 and 0 <= test_acc <= 1
+  fwd_nfe = int(out.splitlines()[0].split('forward nfe ')[1].split(',')[0])
+  assert fwd_nfe == 8                      # 2 rk4 steps x 4 stages in the training forward
 
 
 def test_adjoint_gradients_close_to_direct_gradients():
@@ -127,5 +155,4 @@ def test_adjoint_gradients_close_to_direct_gradients():
     grads[adjoint] = [xd.grad.clone()] + [dict(block.named_parameters())[k].grad.clone() for k in NAMES['transformer']]
     nfe_after_backward = block.odefunc.nfe
     assert nfe_after_backward > 8 or not adjoint      # the adjoint pass evaluates the function again (bm meter)
-  for a, b in zip(grads[False], grads[True]):
-    C.assert_close(b, a, 5e-2, 'adjoint vs direct')
+  assert_grads_close(grads[True], grads[False], 5e-2, ['x'] + NAMES['transformer'])
