@@ -101,7 +101,7 @@ def build_workload(name, device, seed=0):
   from __graft_entry__ import load_package
   load_package()
   from graph_neural_pde_b200.synthetic import SyntheticDataset, baseline_opt
-  ds = SyntheticDataset(name.split('-')[0], seed=seed, num_features=8)   # features are not on the path
+  ds = SyntheticDataset({'Cora-BLEND': 'Cora'}.get(name, name), seed=seed, num_features=8)   # features: not on the path
   key = {'ogbn-arxiv': 'C5', 'Cora': 'C2', 'Photo': 'C3', 'Cora-BLEND': 'C4'}[name]
   opt = baseline_opt(key)
   n = ds.data.num_nodes
