@@ -149,7 +149,12 @@ class ShardedTransformerRHS:
       raise NotImplementedError('reweight_attention is not wired into the sharded path')
     self.spec = func.multihead_att_layer.spec(self.engine)
     self.ws = self.engine.workspace(self.spec)
+    ad = self.spec.ad_eff
+    self.send_buf_k = torch.empty((max(len(p.send_index), 1), ad), dtype=torch.float32, device=self.device)
+    # [n_cols, ad] view of the engine's K workspace: its halo section is a receive buffer of the exchange
+    self.k_view = self.engine._ws_keep['k'][:p.n_cols * ad].view(p.n_cols, ad)
     self._bufs = {}
+    self._graphs = {}
 
   # ---- buffers: [n_cols, d] with the own rows first ---------------------------------------------------------
   def buffer(self, name):
@@ -169,22 +174,24 @@ class ShardedTransformerRHS:
     return buf
 
   # ---- one RHS evaluation -------------------------------------------------------------------------------------
-  def refresh_halo(self, x):
-    p = self.part
-    if self.world == 1 or (p.n_halo == 0 and len(p.send_index) == 0):
-      return
-    stream = N.current_stream(self.device)
-    if len(p.send_index):
-      N.check(N.lib().grand_pack_rows(x.data_ptr(), self.send_index.data_ptr(), len(p.send_index), self.d,
-                                      self.send_buf.data_ptr(), stream))
-    exchange_halo(self.send_buf[:len(p.send_index)], x[p.n_own:], p.send_counts, p.recv_counts, self.group)
-
   def rhs(self, x, ep):
-    """x: [n_cols, d] buffer whose own rows are current; refreshes the halo rows, then projection + fused edges."""
-    self.refresh_halo(x)
+    """x: [n_cols, d] buffer whose own rows are current.  Projects the own rows (Q, K), ships the boundary rows of X
+    AND of K to the ranks that reference them (K_j travels with X_j: ad floats more per row instead of re-projecting
+    every halo row on every rank), then runs the fused edge kernel over the local graph."""
+    p = self.part
     lib, stream = N.lib(), N.current_stream(self.device)
     g, a = C.byref(self.plan.struct()), C.byref(self.spec.struct)
-    N.check(lib.grand_project_qk(x.data_ptr(), self.part.n_own, self.part.n_cols, a, self.ws.q, self.ws.k, stream))
+    ad = self.spec.ad_eff
+    N.check(lib.grand_project_qk(x.data_ptr(), p.n_own, p.n_own, a, self.ws.q, self.ws.k, stream))
+    if self.world > 1 and (p.n_halo or len(p.send_index)):
+      n_send = len(p.send_index)
+      if n_send:
+        N.check(lib.grand_pack_rows(x.data_ptr(), self.send_index.data_ptr(), n_send, self.d,
+                                    self.send_buf.data_ptr(), stream))
+        N.check(lib.grand_pack_rows(self.ws.k, self.send_index.data_ptr(), n_send, ad, self.send_buf_k.data_ptr(),
+                                    stream))
+      exchange_halo(self.send_buf[:n_send], x[p.n_own:], p.send_counts, p.recv_counts, self.group)
+      exchange_halo(self.send_buf_k[:n_send], self.k_view[p.n_own:], p.send_counts, p.recv_counts, self.group)
     N.check(lib.grand_rhs_attention_edges(g, a, x.data_ptr(), C.byref(self.ws), C.byref(ep), stream))
 
   def epilogue(self, x0, **outputs):
@@ -215,12 +222,35 @@ class ShardedTransformerRHS:
       cur, nxt = nxt, cur
     return cur
 
-  def forward_block(self, x_own, x0_own, opt, use_graph=False):
-    """Block forward over [0, T] for this rank's rows: returns z for the own rows."""
+  def forward_block(self, x_own, x0_own, opt, use_graph=True):
+    """Block forward over [0, T] for this rank's rows: returns z for the own rows (a view of a persistent buffer).
+    With `use_graph` the whole stage loop -- kernels AND the NCCL exchanges -- is captured into one CUDA Graph on the
+    second call and replayed afterwards (every rank must make the same sequence of calls)."""
     dts, _ = fixed_grid_dts(0.0, opt['time'], opt['step_size'])
+    method = opt['method']
     y = self.buffer('y')
     self.own(y).copy_(x_own)
     x0 = self.buffer('x0')
     self.own(x0).copy_(x0_own)
-    out = self.integrate_fixed(y, x0, opt['method'], dts)
-    return self.own(out)
+    if not use_graph:
+      return self.own(self.integrate_fixed(y, x0, method, dts))
+    key = (method, tuple(dts))
+    entry = self._graphs.get(key)
+    if entry is None:                       # first call: eager (warms up NCCL and the kernels)
+      out = self.integrate_fixed(y, x0, method, dts)
+      self._graphs[key] = ('warm', out)
+      return self.own(out)
+    if entry[0] == 'warm':
+      saved = self.own(y).clone()
+      torch.cuda.synchronize(self.device)
+      graph = torch.cuda.CUDAGraph()
+      nfe = self.func.nfe
+      with torch.cuda.graph(graph):
+        out = self.integrate_fixed(y, x0, method, dts)
+      self.func.nfe = nfe
+      self.own(y).copy_(saved)
+      entry = ('graph', out, graph)
+      self._graphs[key] = entry
+    self.func._bump_nfe({'euler': 1, 'midpoint': 2, 'rk4': 4}[method] * len(dts))
+    entry[2].replay()
+    return self.own(entry[1])
