@@ -267,6 +267,7 @@ def run_native_single(args):
     torch.cuda.synchronize()
     ms_step = a.elapsed_time(b) / args.steps
     # ---- timed region 2: end to end through the block API from pinned host buffers ----
+    # (a) serial: H2D -> block(x) -> D2H one after the other on one stream
     for _ in range(2):
       step_e2e()
     torch.cuda.synchronize()
@@ -276,7 +277,51 @@ def run_native_single(args):
       step_e2e()
     b2.record()
     torch.cuda.synchronize()
-    ms_e2e = a2.elapsed_time(b2) / args.steps
+    ms_e2e_serial = a2.elapsed_time(b2) / args.steps
+    # (b) pipelined: the same per-step work (H2D of x, block(x), D2H of z, all inside the timed region), double
+    #     buffered so that the copies of neighbouring steps overlap the compute on the two copy engines
+    cur = torch.cuda.current_stream()
+    h2d, d2h = torch.cuda.Stream(), torch.cuda.Stream()
+    xin = [x_dev, torch.empty_like(x_dev)]
+    zout = [torch.empty_like(x_dev), torch.empty_like(x_dev)]
+    zpin = [z_pinned, torch.empty_like(z_pinned).pin_memory()]
+    in_ready = [torch.cuda.Event(), torch.cuda.Event()]
+    in_free = [torch.cuda.Event(), torch.cuda.Event()]
+    out_ready = [torch.cuda.Event(), torch.cuda.Event()]
+    out_free = [torch.cuda.Event(), torch.cuda.Event()]
+
+    def pipelined(count):
+      for b_ in (0, 1):
+        in_free[b_].record(cur)
+        out_free[b_].record(d2h)
+      for it in range(count):
+        b_ = it & 1
+        with torch.cuda.stream(h2d):
+          h2d.wait_event(in_free[b_])
+          xin[b_].copy_(x_pinned, non_blocking=True)
+          in_ready[b_].record(h2d)
+        cur.wait_event(in_ready[b_])
+        cur.wait_event(out_free[b_])
+        func.nfe = 0
+        block.set_x0(xin[b_])
+        with torch.no_grad():
+          zout[b_].copy_(block(xin[b_]))
+        in_free[b_].record(cur)
+        out_ready[b_].record(cur)
+        with torch.cuda.stream(d2h):
+          d2h.wait_event(out_ready[b_])
+          zpin[b_].copy_(zout[b_], non_blocking=True)
+          out_free[b_].record(d2h)
+      cur.wait_stream(d2h)
+
+    pipelined(2)
+    torch.cuda.synchronize()
+    a5, b5 = ev(), ev()
+    a5.record()
+    pipelined(args.steps)
+    b5.record()
+    torch.cuda.synchronize()
+    ms_e2e = a5.elapsed_time(b5) / args.steps
     # ---- dominant kernel on its own: the fused edge kernel with the four rk4 stage epilogues ----
     ws = eng.workspace(prob.spec)
     n_planes = 5
@@ -367,13 +412,21 @@ def run_native_single(args):
                    % (working_set_mb, L2_MB),
       'parallelism': 'single GPU', 'weights': 'trained-like N(0,1/d), seed 0'}),
     'e2e': {'value': e * heads * evals / (ms_e2e * 1e-3), 'unit': UNIT, 'ms_per_step': ms_e2e,
-            'h2d_bytes_per_step': int(x_pinned.numel() * 4), 'd2h_bytes_per_step': int(z_pinned.numel() * 4)},
+            'h2d_bytes_per_step': int(x_pinned.numel() * 4), 'd2h_bytes_per_step': int(z_pinned.numel() * 4),
+            'mode': 'double-buffered: every step copies x from pinned host memory, runs block(x) and copies z back; '
+                    'the copies of step i+-1 overlap the compute of step i on the copy engines',
+            'serial_ms_per_step': ms_e2e_serial, 'serial_value': e * heads * evals / (ms_e2e_serial * 1e-3)},
     'gpu_launches': launches_per_step * args.steps,
     'gpu_launches_per_step': launches_per_step,
     'clocks': clock_summary,
     'roofline': {'bound': 'hbm', 'kernel': 'rhs_kernel<MODE_FUSED,4,1> (+ split_tile_stats pre-pass)',
                  'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak, 'traffic': traffic,
                  'peak_source': peak_src, 'algorithmic_bytes_per_launch': edge_bytes,
+                 'note': 'algorithmic bytes follow SURVEY.md 8(d) (RHS only); the kernel additionally streams the rk4 '
+                         'stage-combine operands the reference moves in separate axpy kernels (avg 2.5 reads + 1.75 '
+                         'writes of [N,d] per launch), see fused_stream_bytes',
+                 'fused_stream_bytes': int(4.25 * n * d * 4),
+                 'frac_incl_fused_streams': (edge_bytes + 4.25 * n * d * 4) / (ms_edge_group * 1e-3) / 1e9 / peak,
                  'us_per_launch': ms_edge_group * 1e3, 'projection_us_per_launch': ms_proj * 1e3,
                  'projection_algorithmic_bytes': proj_bytes,
                  'projection_achieved_GBs': proj_bytes / (ms_proj * 1e-3) / 1e9,

@@ -5,6 +5,9 @@
 // register-tiled fp32 FFMA kernel: the whole [2 ad, d] weight lives in shared memory for the lifetime of a
 // persistent CTA, X row tiles stream through shared memory, every thread owns an RT x OT output block.
 // fp32 FFMA on purpose: the parity bar is 1e-5 of the reference's fp32 GEMM, which a single TF32 pass cannot meet.
+#include <stdlib.h>
+#include <string.h>
+
 #include "common.cuh"
 
 namespace grand {
@@ -133,9 +136,26 @@ project_qk_kernel(const float* __restrict__ x, int n_rows, int n_cols, int d, in
   }
 }
 
+int launch_project_qk_mma(const float* x, int n_rows, int n_cols, int d, const float* wq, const float* bq,
+                          const float* wk, const float* bk, int ad, float* q, float* k, cudaStream_t stream);
+
+// GRAND_PROJ=ffma forces the fp32 FFMA kernel (A/B and fallback); default: 3xTF32 tensor-core kernel where it applies
+static bool use_mma() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("GRAND_PROJ");
+    v = (e != nullptr && !strcmp(e, "ffma")) ? 0 : 1;
+  }
+  return v == 1;
+}
+
 int launch_project_qk(const float* x, int n_rows, int n_cols, int d, const float* wq, const float* bq,
                       const float* wk, const float* bk, int ad, float* q, float* k, cudaStream_t stream) {
   if (n_cols <= 0) return GRAND_OK;
+  if (use_mma()) {
+    const int rc = launch_project_qk_mma(x, n_rows, n_cols, d, wq, bq, wk, bk, ad, q, k, stream);
+    if (rc != GRAND_EUNSUPPORTED) return rc;
+  }
   constexpr int RT = 4, OT = 4;
   const int out = 2 * ad;
   const int tx_count = (out + OT - 1) / OT;

@@ -71,8 +71,7 @@ class AttentionSpec:
     self.struct = a
     self.ad_eff = 2 * a.ad if score == 'exp_kernel2' else a.ad
     self.heads = a.heads
-    self.fused = (score == 'scaled_dot' and a.norm_type == N.NORM_SOFTMAX and a.norm_idx == 0
-                  and a.heads <= N.GRAND_MAX_HEADS)
+    self.fused = score == 'scaled_dot' and a.norm_type == N.NORM_SOFTMAX and a.norm_idx == 0
 
 
 class RhsEngine:
