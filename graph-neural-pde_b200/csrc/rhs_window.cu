@@ -76,15 +76,41 @@ split_tile_stats_kernel(GraphView g, AttnView a, const float* __restrict__ q, co
   old = __shfl_sync(kFull, old, 0);
   if (old != slot1 - slot0 - 1) return;
   __threadfence();
-  // last chunk of the row: l = sum_t l_t exp(m_t - m)
+  // last chunk of the row merges the per-chunk pairs: m = max_t m_t, l = sum_t l_t exp(m_t - m).  One pass with a
+  // running (m, l) per lane over (chunk, head) items -- 8-byte loads, four in flight -- then a shuffle merge; the
+  // longest row of ogbn-arxiv has ~330 chunks and this merge is the tail of the kernel.
+  const float2* pairs = reinterpret_cast<const float2*>(split_stats);
   for (int h = 0; h < H; ++h) {
-    float m = -INFINITY;
-    for (int u = slot0 + lane; u < slot1; u += kWarp) m = fmaxf(m, __ldcg(split_stats + ((size_t)u * H + h) * 2));
-    m = warp_max(m);
-    float l = 0.f;
-    for (int u = slot0 + lane; u < slot1; u += kWarp)
-      l += __ldcg(split_stats + ((size_t)u * H + h) * 2 + 1) * expf(__ldcg(split_stats + ((size_t)u * H + h) * 2) - m);
-    l = warp_sum(l);
+    float m = -INFINITY, l = 0.f;
+    int u = slot0 + lane;
+    for (; u + 3 * kWarp < slot1; u += 4 * kWarp) {
+      float2 p[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) p[i] = __ldcg(pairs + (size_t)(u + i * kWarp) * H + h);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float mn = fmaxf(m, p[i].x);
+        l = l * expf(m - mn) + p[i].y * expf(p[i].x - mn);
+        m = mn;
+      }
+    }
+    for (; u < slot1; u += kWarp) {
+      const float2 p = __ldcg(pairs + (size_t)u * H + h);
+      const float mn = fmaxf(m, p.x);
+      l = l * expf(m - mn) + p.y * expf(p.x - mn);
+      m = mn;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float mo = __shfl_xor_sync(kFull, m, o), lo2 = __shfl_xor_sync(kFull, l, o);
+      const float mn = fmaxf(m, mo);
+      // lanes that saw no chunk carry (m, l) = (-inf, 0): exp(-inf - mn) = 0 keeps them neutral (mn is finite once any
+      // lane has data; two empty lanes give exp(nan)*0 -> guard)
+      const float a = (m == -INFINITY) ? 0.f : l * expf(m - mn);
+      const float b = (mo == -INFINITY) ? 0.f : lo2 * expf(mo - mn);
+      l = a + b;
+      m = mn;
+    }
     if (lane == 0) {
       row_stats[((size_t)split * H + h) * 2 + 0] = m;
       row_stats[((size_t)split * H + h) * 2 + 1] = l;
@@ -385,7 +411,35 @@ rhs_window_kernel(const __grid_constant__ RhsArgs A) {
     for (int r = 0; r < R; ++r)
 #pragma unroll
       for (int v = 0; v < VEC; ++v) acc[r][v] = 0.f;
-    for (int u = slot0; u < slot1; ++u) {
+    // slot order is fixed => deterministic; eight partial rows are requested before the first is added (the longest
+    // row of ogbn-arxiv has ~330 partials: a dependent load per iteration would serialise ~100 us of L2 latency)
+    constexpr int kPB = (R == 1) ? 8 : 2;
+    int u = slot0;
+    for (; u + kPB <= slot1; u += kPB) {
+      float pv[kPB][R][VEC];
+#pragma unroll
+      for (int b = 0; b < kPB; ++b) {
+        const float* pu = A.split_partial + (size_t)(u + b) * d;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          const int c = (lane + r * kWarp) * VEC;
+          if (VEC == 4) {
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (c < d) v = __ldcg(reinterpret_cast<const float4*>(pu + c));
+            pv[b][r][0] = v.x; pv[b][r][1 % VEC] = v.y; pv[b][r][2 % VEC] = v.z; pv[b][r][3 % VEC] = v.w;
+          } else {
+            pv[b][r][0] = c < d ? __ldcg(pu + c) : 0.f;
+          }
+        }
+      }
+#pragma unroll
+      for (int b = 0; b < kPB; ++b)
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+#pragma unroll
+          for (int v = 0; v < VEC; ++v) acc[r][v] += pv[b][r][v];
+    }
+    for (; u < slot1; ++u) {
       const float* pu = A.split_partial + (size_t)u * d;
 #pragma unroll
       for (int r = 0; r < R; ++r) {
