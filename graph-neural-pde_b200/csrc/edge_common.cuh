@@ -55,6 +55,7 @@ struct RhsArgs {
   float* split_partial;      // [n_split_tiles, d]
   int* split_counter;        // [n_split_rows]
   int l2_hints;              // bit 0: evict_last on the gathers, bit 1: evict_first on the streams
+  int tile_begin, tile_end;  // window range of this launch (chunk tiles and packed windows may go to different streams)
 };
 
 // ---- shared-memory async copies and mbarrier -----------------------------------------------------------------

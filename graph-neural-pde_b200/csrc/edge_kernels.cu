@@ -194,6 +194,36 @@ static int check_graph(const grand_graph* g) {
 
 int launch_rhs_mode(int mode, const RhsArgs& A, cudaStream_t stream);
 
+// One non-blocking side stream + fork/join events per device, created on first use and kept for the life of the
+// process (the only state this library owns; GRAND_FORK=0 disables the fork).
+struct SideStream {
+  cudaStream_t stream;
+  cudaEvent_t fork, join;
+};
+static SideStream* side_stream() {
+  static SideStream table[16];
+  static bool ready[16] = {false};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return nullptr;
+  if (!ready[dev]) {
+    // creation is not a stream operation; if a capture is in progress on the calling stream it is unaffected, but
+    // the warm-up call every user makes before capturing creates these anyway
+    if (cudaStreamCreateWithFlags(&table[dev].stream, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+    if (cudaEventCreateWithFlags(&table[dev].fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    if (cudaEventCreateWithFlags(&table[dev].join, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    ready[dev] = true;
+  }
+  return &table[dev];
+}
+static bool fork_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("GRAND_FORK");
+    v = (e != nullptr && atoi(e) == 0) ? 0 : 1;
+  }
+  return v == 1;
+}
+
 // GRAND_L2_HINTS=0..3 (bit 0 evict_last gathers, bit 1 evict_first streams); default from round-1 measurements
 static int l2_hints() {
   static int v = -1;
@@ -262,13 +292,30 @@ int rhs_attention_impl(const grand_graph* g, const grand_attention* a, const flo
                            stream);
     if (rc != GRAND_OK) return rc;
   }
+  A.tile_begin = 0;
+  A.tile_end = g->n_tiles;
   if (fused_ok(A.a)) {
-    if (g->n_split_tiles > 0) {
-      GRAND_REQUIRE(ws->split_stats != nullptr && ws->row_stats != nullptr, GRAND_EINVAL,
-                    "graph has split rows: workspace split_stats / row_stats are null");
-      if ((rc = launch_split_stats(A, stream)) != GRAND_OK) return rc;
+    if (g->n_split_tiles == 0) return launch_rhs_mode(MODE_FUSED, A, stream);
+    GRAND_REQUIRE(ws->split_stats != nullptr && ws->row_stats != nullptr, GRAND_EINVAL,
+                  "graph has split rows: workspace split_stats / row_stats are null");
+    // Fork: the packed windows (whole short rows) do not need the long-row statistics, so they run on a side stream
+    // while this stream does  statistics pre-pass -> chunk tiles;  both kernels are latency-bound on their own and
+    // overlap well.  The fork/join is plain event plumbing and is captured into CUDA Graphs like any other work.
+    SideStream* ss = side_stream();
+    const bool fork = ss != nullptr && fork_enabled() && g->n_tiles > g->n_split_tiles;
+    if (fork) {
+      GRAND_CUDA_OK(cudaEventRecord(ss->fork, stream));
+      GRAND_CUDA_OK(cudaStreamWaitEvent(ss->stream, ss->fork, 0));
+      RhsArgs P = A;
+      P.tile_begin = g->n_split_tiles;
+      if ((rc = launch_rhs_mode(MODE_FUSED, P, ss->stream)) != GRAND_OK) return rc;
+      GRAND_CUDA_OK(cudaEventRecord(ss->join, ss->stream));
+      A.tile_end = g->n_split_tiles;
     }
-    return launch_rhs_mode(MODE_FUSED, A, stream);
+    if ((rc = launch_split_stats(A, stream)) != GRAND_OK) return rc;
+    if ((rc = launch_rhs_mode(MODE_FUSED, A, stream)) != GRAND_OK) return rc;
+    if (fork) GRAND_CUDA_OK(cudaStreamWaitEvent(stream, ss->join, 0));
+    return GRAND_OK;
   }
   if ((rc = run_general_prepass(A.g, A.a, ws, stream)) != GRAND_OK) return rc;
   return launch_rhs_mode(MODE_PRECOMP, A, stream);
@@ -322,6 +369,8 @@ int rhs_laplacian_impl(const grand_graph* g, int d, const float* x, const float*
   A.x = x; A.q = nullptr; A.k = nullptr; A.w_csr = w_csr;
   A.scores = nullptr; A.seg_stats = nullptr; A.gmax = nullptr; A.split_stats = nullptr; A.row_stats = nullptr;
   A.l2_hints = l2_hints();
+  A.tile_begin = 0;
+  A.tile_end = g->n_tiles;
   A.split_partial = ws ? ws->split_partial : nullptr;
   A.split_counter = ws ? ws->split_counter : nullptr;
   return launch_rhs_mode(MODE_WEIGHT, A, stream);

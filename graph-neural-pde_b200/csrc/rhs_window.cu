@@ -220,8 +220,8 @@ rhs_window_kernel(const __grid_constant__ RhsArgs A) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
-  const int t = blockIdx.x * kRhsWarps + warp;
-  if (t >= A.g.n_tiles) return;
+  const int t = A.tile_begin + blockIdx.x * kRhsWarps + warp;
+  if (t >= A.tile_end) return;
   const int d = A.d;
   const int row_bytes = d * (int)sizeof(float);
 
@@ -476,7 +476,8 @@ static int stage_mode() {
 
 template <int MODE, int VEC, int R, int STAGE>
 static int launch_rhs_inst(const RhsArgs& A, cudaStream_t stream) {
-  const int grid = (A.g.n_tiles + kRhsWarps - 1) / kRhsWarps;
+  const int grid = (A.tile_end - A.tile_begin + kRhsWarps - 1) / kRhsWarps;
+  if (grid <= 0) return GRAND_OK;
   size_t smem = 0;
   if (STAGE != STAGE_DIRECT) smem = (size_t)kRhsWarps * ((size_t)GRAND_TILE * A.d * sizeof(float) + 16);
   auto kern = rhs_window_kernel<MODE, VEC, R, STAGE>;
@@ -505,7 +506,7 @@ static int launch_rhs_stage(const RhsArgs& A, cudaStream_t stream) {
 template <int MODE>
 static int launch_rhs_mode_t(const RhsArgs& A, cudaStream_t stream) {
   const int d = A.d;
-  if (A.g.n_tiles == 0) return GRAND_OK;
+  if (A.tile_end <= A.tile_begin) return GRAND_OK;
   if ((d & 3) == 0) {
     const int chunks = (d / 4 + kWarp - 1) / kWarp;
     if (chunks <= 1) return launch_rhs_stage<MODE, 4, 1>(A, stream);
