@@ -195,7 +195,7 @@ static int check_graph(const grand_graph* g) {
 int launch_rhs_mode(int mode, const RhsArgs& A, cudaStream_t stream);
 
 // One non-blocking side stream + fork/join events per device, created on first use and kept for the life of the
-// process (the only state this library owns; GRAND_FORK=0 disables the fork).
+// process (the only state this library owns; GRAND_FORK=1 enables the fork).
 struct SideStream {
   cudaStream_t stream;
   cudaEvent_t fork, join;
@@ -219,7 +219,8 @@ static bool fork_enabled() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("GRAND_FORK");
-    v = (e != nullptr && atoi(e) == 0) ? 0 : 1;
+    v = (e != nullptr && atoi(e) != 0) ? 1 : 0;   // off by default: measured no gain on B200 (profiles/r01d), both
+                                                   // kernels already fill every SM with resident warps
   }
   return v == 1;
 }
