@@ -399,7 +399,7 @@ def run_native_single(args):
     sec = float('nan')
   else:
     sec = time_cpu_reference(cpu_func, x_host, float(opt['step_size']), 1, 1, 2)
-  cpu_value = e * heads * 4 / sec
+  cpu_value = None if args.skip_cpu else e * heads * 4 / sec
 
   value = e * heads * evals / (ms_step * 1e-3)
   line = {
@@ -435,7 +435,7 @@ def run_native_single(args):
                  'stage_mode': os.environ.get('GRAND_STAGE', 'default')},
     'cpu_baseline': {'value': cpu_value, 'unit': UNIT, 'cores': threads, 'kind': 'port',
                      'sample': '2 timed samples of 1 rk4 step = 4 RHS evals of the oracle (torch CPU ops)',
-                     'ms_per_rhs_eval': sec * 1e3 / 4},
+                     'ms_per_rhs_eval': None if args.skip_cpu else sec * 1e3 / 4},
   }
   print(json.dumps(line), flush=True)
 
