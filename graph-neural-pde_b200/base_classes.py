@@ -135,23 +135,40 @@ class ODEblock(nn.Module):
   def set_time(self, time):
     self.t = torch.tensor([0, time]).to(self.device)
 
-  def _integrate(self, x, integrator_options, adjoint_options):
-    """Shared tail of ConstantODEblock.forward / AttODEblock.forward
-    (reference src/block_constant.py:35-70, src/block_transformer_attention.py:36-72)."""
-    t = self.t.type_as(x)
-    integrator = self.train_integrator if self.training else self.test_integrator
+  # ---- helpers shared by the concrete blocks -------------------------------------------------------------------
+  def rebuild_function(self, odefunc_cls, data):
+    """The reference's blocks construct a second function after the base class made one; the first
+    stays alive inside `reg_odefunc` with its own parameters and state_dict keys."""
+    width = self.aug_dim * self.opt['hidden_dim']
+    self.odefunc = odefunc_cls(width, width, self.opt, data, self.device)
+
+  def install_graph(self, edge_index, edge_weight):
+    """Hand the normalised graph to both function instances (reference src/block_constant.py:22-24)."""
+    self.odefunc.edge_index = edge_index.to(self.device)
+    self.odefunc.edge_weight = edge_weight.to(self.device)
+    self.reg_odefunc.odefunc.edge_index = self.odefunc.edge_index
+    self.reg_odefunc.odefunc.edge_weight = self.odefunc.edge_weight
+
+  def use_default_integrators(self):
+    from .odeint import odeint, odeint_adjoint
+    chosen = odeint_adjoint if self.opt['adjoint'] else odeint
+    self.train_integrator = chosen
+    self.test_integrator = chosen
+    self.set_tol()
+
+  def integrate(self, x, solver_options, adjoint_options):
+    """Tail of every block's forward (reference src/block_constant.py:35-70, src/block_transformer_attention.py:36-72):
+    pick the integrator by mode, call it with the reference's keyword set, return the state at t[1].
+    `adjoint_options` is a callable so that options the reference only reads in adjoint training are only read then."""
     if self.training and self.nreg > 0:
       raise NotImplementedError('RNODE regularisers are outside the grand_b200 hot path')
-    func, state = self.odefunc, x
-    if self.opt["adjoint"] and self.training:
-      state_dt = integrator(func, state, t, method=self.opt['method'], options=integrator_options,
-                            adjoint_method=self.opt['adjoint_method'], adjoint_options=adjoint_options(),
-                            atol=self.atol, rtol=self.rtol, adjoint_atol=self.atol_adjoint,
-                            adjoint_rtol=self.rtol_adjoint)
-    else:
-      state_dt = integrator(func, state, t, method=self.opt['method'], options=integrator_options, atol=self.atol,
-                            rtol=self.rtol)
-    return state_dt[1]
+    integrator = self.train_integrator if self.training else self.test_integrator
+    kwargs = dict(method=self.opt['method'], options=solver_options, atol=self.atol, rtol=self.rtol)
+    if self.opt['adjoint'] and self.training:
+      kwargs.update(adjoint_method=self.opt['adjoint_method'], adjoint_options=adjoint_options(),
+                    adjoint_atol=self.atol_adjoint, adjoint_rtol=self.rtol_adjoint)
+    trajectory = integrator(self.odefunc, x, self.t.type_as(x), **kwargs)
+    return trajectory[1]
 
   def __repr__(self):
     return self.__class__.__name__ + '( Time Interval ' + str(self.t[0].item()) + ' -> ' + str(self.t[1].item()) \
@@ -171,26 +188,31 @@ class BaseGNN(nn.Module):
     self.device = device
     self.fm = Meter()
     self.bm = Meter()
+    # layers in the reference's creation order and under the reference's names (state_dict compatibility);
+    # opt['hidden_dim'] is rewritten in place exactly where the reference rewrites it (src/base_classes.py:113,122)
     if opt['beltrami']:
-      self.mx = nn.Linear(self.num_features, opt['feat_hidden_dim'])
-      self.mp = nn.Linear(opt['pos_enc_dim'], opt['pos_enc_hidden_dim'])
+      self._add_linear('mx', self.num_features, opt['feat_hidden_dim'])
+      self._add_linear('mp', opt['pos_enc_dim'], opt['pos_enc_hidden_dim'])
       opt['hidden_dim'] = opt['feat_hidden_dim'] + opt['pos_enc_hidden_dim']
     else:
-      self.m1 = nn.Linear(self.num_features, opt['hidden_dim'])
-    if self.opt['use_mlp']:
-      self.m11 = nn.Linear(opt['hidden_dim'], opt['hidden_dim'])
-      self.m12 = nn.Linear(opt['hidden_dim'], opt['hidden_dim'])
+      self._add_linear('m1', self.num_features, opt['hidden_dim'])
+    if opt['use_mlp']:
+      for name in ('m11', 'm12'):
+        self._add_linear(name, opt['hidden_dim'], opt['hidden_dim'])
     if opt['use_labels']:
-      opt['hidden_dim'] = opt['hidden_dim'] + dataset.num_classes
+      opt['hidden_dim'] += dataset.num_classes
     else:
       self.hidden_dim = opt['hidden_dim']
     if opt['fc_out']:
-      self.fc = nn.Linear(opt['hidden_dim'], opt['hidden_dim'])
-    self.m2 = nn.Linear(opt['hidden_dim'], dataset.num_classes)
-    if self.opt['batch_norm']:
-      self.bn_in = torch.nn.BatchNorm1d(opt['hidden_dim'])
-      self.bn_out = torch.nn.BatchNorm1d(opt['hidden_dim'])
+      self._add_linear('fc', opt['hidden_dim'], opt['hidden_dim'])
+    self._add_linear('m2', opt['hidden_dim'], dataset.num_classes)
+    if opt['batch_norm']:
+      for name in ('bn_in', 'bn_out'):
+        setattr(self, name, torch.nn.BatchNorm1d(opt['hidden_dim']))
     self.regularization_fns, self.regularization_coeffs = create_regularization_fns(self.opt)
+
+  def _add_linear(self, name, n_in, n_out):
+    setattr(self, name, nn.Linear(n_in, n_out))
 
   def getNFE(self):
     return self.odeblock.odefunc.nfe + self.odeblock.reg_odefunc.odefunc.nfe

@@ -24,13 +24,11 @@ if __package__ in (None, ''):   # executed as a script: register the hyphen-name
   sys.path.insert(0, os.path.abspath(os.path.join(os.path.dirname(__file__), '..')))
   from __graft_entry__ import load_package
   load_package()
-  from graph_neural_pde_b200.GNN import GNN
-  from graph_neural_pde_b200.GNN_early import GNNEarly
+  from graph_neural_pde_b200.models import GNN, GNNEarly
   from graph_neural_pde_b200.synthetic import SyntheticDataset, baseline_opt
   from graph_neural_pde_b200.utils import print_model_params
 else:
-  from .GNN import GNN
-  from .GNN_early import GNNEarly
+  from .models import GNN, GNNEarly
   from .synthetic import SyntheticDataset, baseline_opt
   from .utils import print_model_params
 

@@ -19,7 +19,7 @@ from graph_neural_pde_b200.block_transformer_attention import AttODEblock  # noq
 from graph_neural_pde_b200.function_laplacian_diffusion import LaplacianODEFunc  # noqa: E402
 from graph_neural_pde_b200.function_transformer_attention import (ODEFuncTransformerAtt,  # noqa: E402
                                                                    SpGraphTransAttentionLayer)
-from graph_neural_pde_b200.GNN_early import GNNEarly  # noqa: E402
+from graph_neural_pde_b200.models import GNNEarly  # noqa: E402
 from graph_neural_pde_b200.synthetic import Data, default_opt, make_graph  # noqa: E402
 from graph_neural_pde_b200.utils import DummyDataset  # noqa: E402
 
