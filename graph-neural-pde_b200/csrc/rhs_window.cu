@@ -41,17 +41,16 @@ __device__ __forceinline__ float fused_score(const AttnView& a, const float* __r
   return a.inv_sqrt_dk_exact != 0.f ? s * a.inv_sqrt_dk_exact : s / a.sqrt_dk;
 }
 
-// ---- long rows: (max, sum-exp) per head and chunk, merged per row by the last chunk to arrive ---------------------
+// ---- long rows, first step: (max, sum-exp) per head and chunk -------------------------------------------------------
 __global__ void __launch_bounds__(256)
 split_tile_stats_kernel(GraphView g, AttnView a, const float* __restrict__ q, const float* __restrict__ k,
-                        float* __restrict__ split_stats, float* __restrict__ row_stats,
-                        int* __restrict__ split_counter) {
+                        float* __restrict__ split_stats) {
   const int lane = threadIdx.x & 31;
   const int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);   // split tiles are tiles [0, n_split_tiles)
   if (t >= g.n_split_tiles) return;
   const int4 hdr = __ldg(g.win_hdr + t);
   const int2 rec = __ldg(g.win_rec + (size_t)t * kWarp + lane);
-  const int row = hdr.x, cnt = hdr.z >> 8, split = hdr.w;
+  const int row = hdr.x, cnt = hdr.z >> 8;
   const bool valid = lane < cnt;
   const float* kj = k + (size_t)rec.x * a.ad_eff;
   const float* qi = q + (size_t)row * a.ad_eff;
@@ -64,18 +63,20 @@ split_tile_stats_kernel(GraphView g, AttnView a, const float* __restrict__ q, co
     const float m = warp_max(s);
     const float l = warp_sum(valid ? expf(s - m) : 0.f);
     if (lane == 0) {
-      __stcg(split_stats + ((size_t)t * H + h) * 2 + 0, m);
-      __stcg(split_stats + ((size_t)t * H + h) * 2 + 1, l);
+      split_stats[((size_t)t * H + h) * 2 + 0] = m;
+      split_stats[((size_t)t * H + h) * 2 + 1] = l;
     }
   }
-  __threadfence();
-  __syncwarp();
+}
+
+// ---- long rows, second step: one warp per long row merges its chunks' pairs (no fences, no atomics: stream order
+//      between the two small kernels is the synchronisation) ---------------------------------------------------
+__global__ void __launch_bounds__(256)
+split_row_merge_kernel(GraphView g, int H, const float* __restrict__ split_stats, float* __restrict__ row_stats) {
+  const int lane = threadIdx.x & 31;
+  const int split = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (split >= g.n_split_rows) return;
   const int slot0 = __ldg(g.split_tile0 + split), slot1 = __ldg(g.split_tile0 + split + 1);
-  int old = 0;
-  if (lane == 0) old = atomicAdd(split_counter + split, 1);
-  old = __shfl_sync(kFull, old, 0);
-  if (old != slot1 - slot0 - 1) return;
-  __threadfence();
   // last chunk of the row merges the per-chunk pairs: m = max_t m_t, l = sum_t l_t exp(m_t - m).  One pass with a
   // running (m, l) per lane over (chunk, head) items -- 8-byte loads, four in flight -- then a shuffle merge; the
   // longest row of ogbn-arxiv has ~330 chunks and this merge is the tail of the kernel.
@@ -86,7 +87,7 @@ split_tile_stats_kernel(GraphView g, AttnView a, const float* __restrict__ q, co
     for (; u + 3 * kWarp < slot1; u += 4 * kWarp) {
       float2 p[4];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) p[i] = __ldcg(pairs + (size_t)(u + i * kWarp) * H + h);
+      for (int i = 0; i < 4; ++i) p[i] = __ldg(pairs + (size_t)(u + i * kWarp) * H + h);
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const float mn = fmaxf(m, p[i].x);
@@ -95,7 +96,7 @@ split_tile_stats_kernel(GraphView g, AttnView a, const float* __restrict__ q, co
       }
     }
     for (; u < slot1; u += kWarp) {
-      const float2 p = __ldcg(pairs + (size_t)u * H + h);
+      const float2 p = __ldg(pairs + (size_t)u * H + h);
       const float mn = fmaxf(m, p.x);
       l = l * expf(m - mn) + p.y * expf(p.x - mn);
       m = mn;
@@ -116,7 +117,6 @@ split_tile_stats_kernel(GraphView g, AttnView a, const float* __restrict__ q, co
       row_stats[((size_t)split * H + h) * 2 + 1] = l;
     }
   }
-  if (lane == 0) split_counter[split] = 0;
 }
 
 // ---- epilogue: residual + RK stage combine for one finished row -----------------------------------------------------
@@ -531,8 +531,10 @@ int launch_rhs_mode(int mode, const RhsArgs& A, cudaStream_t stream) {
 
 int launch_split_stats(const RhsArgs& A, cudaStream_t stream) {
   if (A.g.n_split_tiles == 0) return GRAND_OK;
-  split_tile_stats_kernel<<<(A.g.n_split_tiles + 7) / 8, 256, 0, stream>>>(A.g, A.a, A.q, A.k, A.split_stats,
-                                                                          A.row_stats, A.split_counter);
+  split_tile_stats_kernel<<<(A.g.n_split_tiles + 7) / 8, 256, 0, stream>>>(A.g, A.a, A.q, A.k, A.split_stats);
+  GRAND_CUDA_OK(cudaGetLastError());
+  count_launch();
+  split_row_merge_kernel<<<(A.g.n_split_rows + 7) / 8, 256, 0, stream>>>(A.g, A.a.heads, A.split_stats, A.row_stats);
   GRAND_CUDA_OK(cudaGetLastError());
   count_launch();
   return GRAND_OK;
