@@ -16,7 +16,7 @@ GRAND_MAX_HEADS = 8
 GRAND_MAX_TERMS = 8
 ABI_VERSION = 1
 
-SCORE_TYPES = {'scaled_dot': 0, 'cosine_sim': 1, 'pearson': 2, 'exp_kernel': 3, 'exp_kernel2': 4}
+SCORE_TYPES = {'scaled_dot': 0, 'cosine_sim': 1, 'pearson': 2, 'exp_kernel': 3, 'exp_kernel2': 4, 'gat': 5}
 NORM_SOFTMAX, NORM_SQUAREPLUS = 0, 1
 METHODS = {'euler': 0, 'midpoint': 1, 'rk4': 2}
 

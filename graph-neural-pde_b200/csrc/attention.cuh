@@ -16,7 +16,7 @@ struct AttnView {
   int norm_idx;
   float sqrt_dk;                  // (float)np.sqrt(d_k): the reference divides by it (:196)
   float inv_sqrt_dk_exact;        // 1/sqrt(d_k) when that is an exact power of two, else 0
-  const float* kernel_scalars;    // device [4]
+  const float* kernel_scalars;    // device [4]; GAT: [2 d_k + 1]
   const float* edge_weight_csr;   // or null
 };
 
@@ -116,6 +116,14 @@ __device__ __forceinline__ float edge_score(const AttnView& a, const float* __re
       const float ssx = head_sqdist<kVec4>(q, k, dk);
       const float ssp = head_sqdist<kVec4>(q + a.ad, k + a.ad, dk);
       return (ovx * ovx) * expf(-ssx / (2.f * (lsx * lsx))) * (ovp * ovp) * expf(-ssp / (2.f * (lsp * lsp)));
+    }
+    case GRAND_SCORE_GAT: {
+      // sum(a * [h_i ; h_j]) over the 2 d_k stacked entries, then LeakyReLU (reference function_GAT_attention.py:111-113)
+      float s = 0.f;
+      for (int c = 0; c < dk; ++c) s = fmaf(__ldg(a.kernel_scalars + c), __ldg(q + c), s);
+      for (int c = 0; c < dk; ++c) s = fmaf(__ldg(a.kernel_scalars + dk + c), __ldg(k + c), s);
+      const float slope = __ldg(a.kernel_scalars + 2 * dk);
+      return s > 0.f ? s : slope * s;
     }
   }
   return 0.f;

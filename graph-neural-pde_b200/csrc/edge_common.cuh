@@ -11,6 +11,7 @@ constexpr int MODE_WEIGHT = 2;    // GRAND-l: per-edge weights given
 constexpr int STAGE_DIRECT = 0;   // neighbour rows straight into registers, a batch at a time
 constexpr int STAGE_CPASYNC = 1;  // cp.async (LDGSTS) into the warp's shared-memory window buffer
 constexpr int STAGE_BULK = 2;     // cp.async.bulk (TMA bulk copy) + mbarrier into the window buffer
+constexpr int STAGE_ROWBUF = 3;   // register batches that ignore row boundaries; finished rows wait in shared memory
 
 // window header written by the host plan (graph_plan.py): one int4 per window
 //   .x first (or only) row   .y first CSR position   .z nrows | cnt << 8   .w split-row index or -1

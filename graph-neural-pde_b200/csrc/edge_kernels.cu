@@ -132,13 +132,15 @@ static GraphView view(const grand_graph* g) {
 int make_attn_view(const grand_attention* a, AttnView* out) {
   GRAND_REQUIRE(a->heads > 0 && a->ad > 0 && a->ad % a->heads == 0, GRAND_EINVAL,
                 "Number of heads (%d) must be a factor of the dimension size (%d)", a->heads, a->ad);
-  GRAND_REQUIRE(a->score_type >= 0 && a->score_type <= GRAND_SCORE_EXP_KERNEL2, GRAND_EINVAL,
+  GRAND_REQUIRE(a->score_type >= 0 && a->score_type <= GRAND_SCORE_GAT, GRAND_EINVAL,
                 "unknown score_type %d", a->score_type);
   GRAND_REQUIRE(a->norm_type == GRAND_NORM_SOFTMAX || a->norm_type == GRAND_NORM_SQUAREPLUS, GRAND_EINVAL,
                 "unknown norm_type %d", a->norm_type);
   GRAND_REQUIRE(a->norm_idx == 0 || a->norm_idx == 1, GRAND_EINVAL, "attention_norm_idx must be 0 or 1");
-  const bool needs_scalars = a->score_type == GRAND_SCORE_EXP_KERNEL || a->score_type == GRAND_SCORE_EXP_KERNEL2;
-  GRAND_REQUIRE(!needs_scalars || a->kernel_scalars != nullptr, GRAND_EINVAL, "exp_kernel needs kernel_scalars");
+  const bool needs_scalars = a->score_type == GRAND_SCORE_EXP_KERNEL || a->score_type == GRAND_SCORE_EXP_KERNEL2 ||
+                             a->score_type == GRAND_SCORE_GAT;
+  GRAND_REQUIRE(!needs_scalars || a->kernel_scalars != nullptr, GRAND_EINVAL,
+                "exp_kernel / GAT scorers need kernel_scalars");
   out->ad = a->ad;
   out->ad_eff = a->score_type == GRAND_SCORE_EXP_KERNEL2 ? 2 * a->ad : a->ad;
   out->heads = a->heads;

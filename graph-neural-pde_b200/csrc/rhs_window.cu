@@ -215,7 +215,7 @@ __device__ __forceinline__ void gather_batch(const float* __restrict__ xl, int d
 
 // ---- the RHS kernel -----------------------------------------------------------------------------------------------------
 template <int MODE, int VEC, int R, int STAGE>
-__global__ void __launch_bounds__(kRhsThreads, STAGE == STAGE_DIRECT ? GRAND_DIRECT_MINBLOCKS : 3)
+__global__ void __launch_bounds__(kRhsThreads, (STAGE == STAGE_DIRECT || STAGE == STAGE_ROWBUF) ? GRAND_DIRECT_MINBLOCKS : 3)
 rhs_window_kernel(const __grid_constant__ RhsArgs A) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31;
@@ -239,7 +239,7 @@ rhs_window_kernel(const __grid_constant__ RhsArgs A) {
   // ---- level 2a: start moving every neighbour row of the window --------------------------------------------------
   float* stage = nullptr;
   uint32_t bar = 0;
-  if (STAGE != STAGE_DIRECT) {
+  if (STAGE == STAGE_CPASYNC || STAGE == STAGE_BULK) {
     const int warp_bytes = GRAND_TILE * row_bytes + 16;
     unsigned char* base = smem_raw + (size_t)warp * warp_bytes;
     stage = reinterpret_cast<float*>(base);
@@ -330,6 +330,85 @@ rhs_window_kernel(const __grid_constant__ RhsArgs A) {
     __syncwarp();
   }
 
+  // ---- STAGE_ROWBUF: the window's edges are gathered in fixed batches that ignore row boundaries (ceil(cnt / NB)
+  //      exposed latencies per window instead of one per power-of-two piece of every row); a finished row's sum waits
+  //      in the warp's shared-memory slot (each lane re-reads only what it wrote: no barrier) for the epilogue ------
+  if (STAGE == STAGE_ROWBUF && split < 0) {
+    float* rowbuf = reinterpret_cast<float*>(smem_raw) + (size_t)warp * GRAND_MAX_PACKED_ROWS * d;
+    const unsigned starts = __ballot_sync(kFull, valid && lo == lane);       // bit e: edge e opens a row
+    const unsigned rowmask =                                                  // bit r: row r of the window has edges
+        __ballot_sync(kFull, lane < nrows && ((rec.y >> 26) & 0x3f) > ((rec.y >> 20) & 0x3f));
+    unsigned remaining = rowmask;
+    int kr = -1;
+    float acc[R][VEC];
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) acc[r][v] = 0.f;
+    constexpr int NB = (kDirectBatch / R) < 2 ? 2 : (kDirectBatch / R);
+    const float* xl = A.x + (size_t)lane * VEC;
+    for (int e = 0; e < cnt; e += NB) {
+      float aa[NB];
+      float4 xv[NB][R];
+#pragma unroll
+      for (int u = 0; u < NB; ++u) {
+        const int eu = e + u;
+        const int ju = __shfl_sync(kFull, j, eu & 31);
+        aa[u] = __shfl_sync(kFull, ab, eu & 31);
+        const float* xr = xl + (size_t)ju * d;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          xv[u][r] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (eu < cnt && (full || (lane + r * kWarp) * VEC < d)) xv[u][r] = ldg4_hint(xr + r * kWarp * VEC, pol_keep);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < NB; ++u) {
+        const int eu = e + u;
+        if (eu < cnt) {
+          if ((starts >> eu) & 1u) {
+            if (kr >= 0) {
+#pragma unroll
+              for (int r = 0; r < R; ++r)
+                if (full || (lane + r * kWarp) * VEC < d)
+                  *reinterpret_cast<float4*>(rowbuf + (size_t)kr * d + (lane + r * kWarp) * VEC) =
+                      make_float4(acc[r][0], acc[r][1 % VEC], acc[r][2 % VEC], acc[r][3 % VEC]);
+            }
+            kr = __ffs(remaining) - 1;
+            remaining &= remaining - 1;
+#pragma unroll
+            for (int r = 0; r < R; ++r)
+#pragma unroll
+              for (int v = 0; v < VEC; ++v) acc[r][v] = 0.f;
+          }
+#pragma unroll
+          for (int r = 0; r < R; ++r) {
+            acc[r][0] = fmaf(aa[u], xv[u][r].x, acc[r][0]); acc[r][1 % VEC] = fmaf(aa[u], xv[u][r].y, acc[r][1 % VEC]);
+            acc[r][2 % VEC] = fmaf(aa[u], xv[u][r].z, acc[r][2 % VEC]); acc[r][3 % VEC] = fmaf(aa[u], xv[u][r].w, acc[r][3 % VEC]);
+          }
+        }
+      }
+    }
+    if (kr >= 0) {
+#pragma unroll
+      for (int r = 0; r < R; ++r)
+        if (full || (lane + r * kWarp) * VEC < d)
+          *reinterpret_cast<float4*>(rowbuf + (size_t)kr * d + (lane + r * kWarp) * VEC) =
+              make_float4(acc[r][0], acc[r][1 % VEC], acc[r][2 % VEC], acc[r][3 % VEC]);
+    }
+    for (int r0 = 0; r0 < nrows; ++r0) {
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (((rowmask >> r0) & 1u) && (full || (lane + r * kWarp) * VEC < d))
+          v = *reinterpret_cast<const float4*>(rowbuf + (size_t)r0 * d + (lane + r * kWarp) * VEC);
+        acc[r][0] = v.x; acc[r][1 % VEC] = v.y; acc[r][2 % VEC] = v.z; acc[r][3 % VEC] = v.w;
+      }
+      finish_row<VEC, R>(A, row0 + r0, lane, alpha, beta, pol_stream, acc);
+    }
+    return;
+  }
+
   for (int kr = 0; kr < nrows; ++kr) {
     int e_lo = 0, e_hi = cnt;
     if (split < 0) {
@@ -343,7 +422,7 @@ rhs_window_kernel(const __grid_constant__ RhsArgs A) {
 #pragma unroll
       for (int v = 0; v < VEC; ++v) acc[r][v] = 0.f;
 
-    if (STAGE != STAGE_DIRECT) {
+    if (STAGE == STAGE_CPASYNC || STAGE == STAGE_BULK) {
       if (full) {
 #pragma unroll 4
         for (int e = e_lo; e < e_hi; ++e) {
@@ -469,6 +548,7 @@ static int stage_mode() {
       if (!strcmp(e, "direct")) mode = STAGE_DIRECT;
       else if (!strcmp(e, "cpasync")) mode = STAGE_CPASYNC;
       else if (!strcmp(e, "bulk")) mode = STAGE_BULK;
+      else if (!strcmp(e, "rowbuf")) mode = STAGE_ROWBUF;
     }
   }
   return mode;
@@ -479,7 +559,8 @@ static int launch_rhs_inst(const RhsArgs& A, cudaStream_t stream) {
   const int grid = (A.tile_end - A.tile_begin + kRhsWarps - 1) / kRhsWarps;
   if (grid <= 0) return GRAND_OK;
   size_t smem = 0;
-  if (STAGE != STAGE_DIRECT) smem = (size_t)kRhsWarps * ((size_t)GRAND_TILE * A.d * sizeof(float) + 16);
+  if (STAGE == STAGE_CPASYNC || STAGE == STAGE_BULK) smem = (size_t)kRhsWarps * ((size_t)GRAND_TILE * A.d * sizeof(float) + 16);
+  if (STAGE == STAGE_ROWBUF) smem = (size_t)kRhsWarps * GRAND_MAX_PACKED_ROWS * A.d * sizeof(float);
   auto kern = rhs_window_kernel<MODE, VEC, R, STAGE>;
   static size_t configured = 48 * 1024;
   if (smem > configured) {
@@ -496,7 +577,14 @@ template <int MODE, int VEC, int R>
 static int launch_rhs_stage(const RhsArgs& A, cudaStream_t stream) {
   // staging needs 16-byte rows and a window buffer that leaves room for >= 2 blocks per SM
   const bool can_stage = VEC == 4 && (size_t)kRhsWarps * GRAND_TILE * A.d * sizeof(float) <= 100 * 1024;
-  const int mode = can_stage ? stage_mode() : STAGE_DIRECT;
+  int mode = stage_mode();
+  if (mode == STAGE_ROWBUF) {   // row buffer: 8 rows per warp; keep >= 6 blocks per SM resident
+    if (VEC != 4 || (size_t)kRhsWarps * GRAND_MAX_PACKED_ROWS * A.d * sizeof(float) > 32 * 1024) mode = STAGE_DIRECT;
+  } else if (!can_stage) {
+    mode = STAGE_DIRECT;
+  }
+  if (VEC == 4 && mode == STAGE_ROWBUF)
+    return launch_rhs_inst<MODE, VEC, R, VEC == 4 ? STAGE_ROWBUF : STAGE_DIRECT>(A, stream);
   if (VEC == 4 && mode == STAGE_BULK) return launch_rhs_inst<MODE, VEC, R, VEC == 4 ? STAGE_BULK : STAGE_DIRECT>(A, stream);
   if (VEC == 4 && mode == STAGE_CPASYNC)
     return launch_rhs_inst<MODE, VEC, R, VEC == 4 ? STAGE_CPASYNC : STAGE_DIRECT>(A, stream);

@@ -2,8 +2,10 @@
 the classifier after every solver step and remember the best validation step.  The attribute chain
 `odeblock.test_integrator.solver.best_{val,test,train,time}` read by run_GNN.main (reference src/run_GNN.py:266-271)
 is kept.  The ODE steps run on the CUDA engine; the per-step classifier read-out (relu -> m2 -> argmax -> masked
-accuracy) is a handful of torch ops with the same three host reads per step as the reference (fusing it on device
-is SURVEY.md 8(f).2)."""
+accuracy -> "is this the best validation step so far") stays on the device: the reference's three `.item()` host reads
+per solver step (src/early_stop_solver.py:203-218) become ONE read of four numbers when the integration ends
+(SURVEY.md 8(f).2).  Accuracies are formed as integer counts divided in float64, i.e. the same values python's
+int / int gives the reference."""
 import torch
 import torch.nn.functional as F
 
@@ -66,10 +68,33 @@ class _EarlyStopSolver:
       return self.test_OGB(z.log_softmax(dim=-1))
     return self.test(z)
 
+  # ---- device-resident scoring ------------------------------------------------------------------------------------
+  def _masks(self, device):
+    if getattr(self, '_mask_cache', None) is None:
+      d = self.data
+      masks = torch.stack([m.to(device).bool() for m in (d.train_mask, d.val_mask, d.test_mask)])
+      self._mask_cache = (masks, masks.sum(dim=1).double(), d.y.to(device).reshape(-1))
+      self._best = torch.zeros(4, dtype=torch.float64, device=device)   # train, val, test, time
+    return self._mask_cache
+
+  @torch.no_grad()
   def _score(self, y1, t1):
-    train_acc, val_acc, test_acc = self.evaluate(y1)
-    if val_acc > self.best_val:
-      self.set_accs(train_acc, val_acc, test_acc, t1)
+    """evaluate() + the `val_acc > best_val` update of the reference (:203-218, :172-176) without host reads."""
+    if not self.m2_weight.shape[1] == y1.shape[1]:  # system has been augmented
+      y1 = torch.split(y1, self.m2_weight.shape[1], dim=1)[0]
+    masks, counts, labels = self._masks(y1.device)
+    pred = F.linear(F.relu(y1), self.m2_weight, self.m2_bias).argmax(dim=-1)   # log_softmax keeps the argmax
+    hits = (pred.reshape(-1) == labels).unsqueeze(0) & masks
+    accs = hits.sum(dim=1).double() / counts
+    cand = torch.cat([accs, torch.full((1,), float(t1), dtype=torch.float64, device=y1.device)])
+    self._best = torch.where(accs[1] > self._best[1], cand, self._best)
+
+  def _publish(self):
+    """the single host read: best_{train,val,test,time} as python floats, as run_GNN.main expects them"""
+    if getattr(self, '_best', None) is not None:
+      train, val, test, time = self._best.tolist()
+      if val > self.best_val:
+        self.set_accs(train, val, test, time)
 
 
 class EarlyStopRK4(_EarlyStopSolver):
@@ -79,6 +104,7 @@ class EarlyStopRK4(_EarlyStopSolver):
   def integrate(self, t):
     solution = integrate_fixed(self.func, self.y0, t, 'rk4', self.options['step_size'],
                                on_step=lambda t0, t1, y0, y1: self._score(y1, t1))
+    self._publish()
     return t[-1], solution
 
 
@@ -92,6 +118,7 @@ class EarlyStopDopri5(_EarlyStopSolver):
 
     solution, _ = integrate_dopri5(self.func, self.y0, t, self.rtol, self.atol, on_step=hook,
                                    max_steps=self.max_test_steps)
+    self._publish()
     return t[-1], solution
 
 

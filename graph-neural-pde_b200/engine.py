@@ -43,7 +43,10 @@ class AttentionSpec:
     a = N.GrandAttention()
     a.d, a.ad, a.heads = int(d), int(layer.attention_dim), int(layer.h)
     att_type = opt['attention_type']
-    if opt['beltrami'] and att_type == 'exp_kernel':
+    if hasattr(layer, 'native_weights'):
+      # layers with their own scorer (GAT: function_GAT_attention.SpGraphAttentionLayer) describe themselves
+      score, wq, bq, wk, bk, scalars = layer.native_weights()
+    elif opt['beltrami'] and att_type == 'exp_kernel':
       score = 'exp_kernel2'
       wq, bq, wk, bk = layer.packed_beltrami_weights()
       scalars = torch.stack([layer.output_var_x.detach().reshape(()), layer.lengthscale_x.detach().reshape(()),
@@ -59,7 +62,7 @@ class AttentionSpec:
     for t in (wq, bq, wk, bk):
       N.require_cuda(t, 'attention weight')
     a.score_type = N.SCORE_TYPES[score]
-    a.norm_type = N.NORM_SQUAREPLUS if opt['square_plus'] else N.NORM_SOFTMAX
+    a.norm_type = N.NORM_SQUAREPLUS if (opt['square_plus'] and score != 'gat') else N.NORM_SOFTMAX   # GAT: softmax only
     a.norm_idx = int(opt['attention_norm_idx'])
     self.keep += [wq, bq, wk, bk, scalars, edge_weight_csr]
     a.wq, a.bq, a.wk, a.bk = (N.ptr(t.detach().contiguous() if not t.is_contiguous() else t.detach())

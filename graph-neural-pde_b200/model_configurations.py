@@ -2,6 +2,8 @@
 hot-path blocks / functions are built; the reference's other registry entries are named and refused."""
 from .block_constant import ConstantODEblock
 from .block_transformer_attention import AttODEblock
+from .block_transformer_hard_attention import HardAttODEblock
+from .function_GAT_attention import ODEFuncAtt
 from .function_laplacian_diffusion import LaplacianODEFunc
 from .function_transformer_attention import ODEFuncTransformerAtt
 
@@ -14,8 +16,8 @@ class FunctionNotDefined(Exception):
   pass
 
 
-_OUT_OF_SCOPE_BLOCKS = ('mixed', 'hard_attention', 'rewire_attention')
-_OUT_OF_SCOPE_FUNCTIONS = ('GAT',)
+_OUT_OF_SCOPE_BLOCKS = ('mixed', 'rewire_attention')
+_OUT_OF_SCOPE_FUNCTIONS = ()
 
 
 def set_block(opt):
@@ -24,6 +26,8 @@ def set_block(opt):
     return AttODEblock
   if ode_str == 'constant':
     return ConstantODEblock
+  if ode_str == 'hard_attention':
+    return HardAttODEblock
   if ode_str in _OUT_OF_SCOPE_BLOCKS:
     raise NotImplementedError('block %r is outside the grand_b200 hot-path scope (SURVEY.md section 8)' % ode_str)
   raise BlockNotDefined
@@ -35,6 +39,8 @@ def set_function(opt):
     return LaplacianODEFunc
   if ode_str == 'transformer':
     return ODEFuncTransformerAtt
+  if ode_str == 'GAT':
+    return ODEFuncAtt
   if ode_str in _OUT_OF_SCOPE_FUNCTIONS:
     raise NotImplementedError('function %r is outside the grand_b200 hot-path scope (SURVEY.md section 8)' % ode_str)
   raise FunctionNotDefined

@@ -35,6 +35,7 @@ extern "C" {
 /* edges per window (one warp, one edge per lane): short rows are packed several to a window, rows with more
  * in-edges are cut into chunks of this size */
 #define GRAND_TILE 32
+#define GRAND_MAX_PACKED_ROWS 8  /* whole rows packed into one window: at most this many */
 #define GRAND_MAX_HEADS 8
 #define GRAND_MAX_TERMS 8
 
@@ -44,7 +45,10 @@ enum grand_score_type {
   GRAND_SCORE_COSINE = 1,      /* CosineSimilarity(eps=1e-5)                        :197-199 */
   GRAND_SCORE_PEARSON = 2,     /* cosine of mean-centred q, k                       :200-206 */
   GRAND_SCORE_EXP_KERNEL = 3,  /* ov^2 exp(-|q-k|^2 / (2 ls^2))                     :193-194 */
-  GRAND_SCORE_EXP_KERNEL2 = 4  /* beltrami: product of a feature and a positional exp kernel :133-169 */
+  GRAND_SCORE_EXP_KERNEL2 = 4, /* beltrami: product of a feature and a positional exp kernel :133-169 */
+  GRAND_SCORE_GAT = 5          /* GAT additive scorer leaky_relu(a_src.h_i + a_dst.h_j), the same `a` for every head:
+                                  reference src/function_GAT_attention.py:105-114.  q = k = x W (wq = wk = W^T, zero
+                                  biases); kernel_scalars = device [2 d_k + 1]: a_src, a_dst, negative slope */
 };
 
 /* normaliser, reference :210-213 and src/utils.py:179-208 */
@@ -95,7 +99,8 @@ typedef struct grand_attention {
   const float* bq;             /* Q.bias   [ad]                                                       */
   const float* wk;             /* K.weight [ad, d]                                                    */
   const float* bk;             /* K.bias   [ad]                                                       */
-  const float* kernel_scalars; /* device [4]: output_var, lengthscale (, output_var_p, lengthscale_p) */
+  const float* kernel_scalars; /* device [4]: output_var, lengthscale (, output_var_p, lengthscale_p);
+                                  GRAND_SCORE_GAT: [2 d_k + 1], see the enum                            */
   const float* edge_weight_csr;/* [n_edges] reweight_attention weights in CSR order, or null (:208-209)*/
 } grand_attention;
 

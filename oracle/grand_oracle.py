@@ -250,6 +250,57 @@ def transformer_rhs(x: Tensor, edge_index: Tensor, P: Dict[str, Tensor], opt: di
   return residual(ax, x, alpha_train, beta_train, x0, opt)
 
 
+def gat_attention_forward(x: Tensor, edge: Tensor, P: Dict[str, Tensor], opt: dict) -> Tuple[Tensor, Tensor]:
+  """SpGraphAttentionLayer.forward -> (attention[E,H], wx[N,ad]); src/function_GAT_attention.py:105-116.
+  P: 'W' [d, ad], 'a' [2 d_k, 1, 1] (shared by the heads), 'Wout' [ad, d] (mix_features only)."""
+  h = int(opt['heads'])
+  ad = P['W'].shape[1]
+  dk = ad // h
+  wx = torch.mm(x, P['W'])                                                        # :106
+  hh = wx.view(-1, h, dk).transpose(1, 2)                                         # [N, d_k, H]  :107-108
+  edge_h = torch.cat((hh[edge[0, :], :, :], hh[edge[1, :], :, :]), dim=1).transpose(0, 1)   # [2 d_k, E, H]  :111-112
+  edge_e = torch.nn.functional.leaky_relu(torch.sum(P['a'] * edge_h, dim=0), opt['leaky_relu_slope'])   # :113
+  attention = segment_softmax(edge_e, edge[opt['attention_norm_idx']])            # :114
+  return attention, wx
+
+
+def gat_rhs(x: Tensor, edge_index: Tensor, P: Dict[str, Tensor], opt: dict, alpha_train: Tensor, beta_train: Tensor,
+            x0: Optional[Tensor] = None) -> Tensor:
+  """ODEFuncAtt.forward without the nfe bookkeeping; src/function_GAT_attention.py:31-64 (per-head spmm, then the
+  mean over heads -- unlike the transformer function, which averages the attention first)."""
+  attention, wx = gat_attention_forward(x, edge_index, P, opt)
+  n = x.shape[0]
+  if opt['mix_features']:                                                         # :32-37
+    agg = torch.mean(torch.stack([spmm(edge_index, attention[:, i], n, n, wx) for i in range(opt['heads'])], dim=0),
+                     dim=0)
+    ax = torch.mm(agg, P['Wout'])
+  else:                                                                           # :38-42
+    ax = torch.mean(torch.stack([spmm(edge_index, attention[:, i], n, n, x) for i in range(opt['heads'])], dim=0),
+                    dim=0)
+  return residual(ax, x, alpha_train, beta_train, x0, opt)
+
+
+def hard_attention_sample(x: Tensor, data_edge_index: Tensor, attention: Tensor, opt: dict, num_nodes: int,
+                          training: bool) -> Tuple[Tensor, Tensor]:
+  """The edge selection of HardAttODEblock.forward (src/block_transformer_hard_attention.py:49-68):
+  -> (odefunc.edge_index, odefunc.attention_weights[E']).  Eval mode keeps every edge with the head-mean attention;
+  training keeps the edges whose (optionally flux-weighted) mean attention exceeds the (1 - att_samp_pct) quantile
+  and renormalises the kept values over edge_index[attention_norm_idx] (:43-46)."""
+  mean_att = attention.mean(dim=1, keepdim=False)
+  if not training:
+    return data_edge_index, mean_att
+  if opt['use_flux']:
+    delta = torch.linalg.norm(x[data_edge_index[0, :], :] - x[data_edge_index[1, :], :], dim=1)
+    mean_att = mean_att * delta
+  threshold = torch.quantile(mean_att, 1 - opt['att_samp_pct'])
+  mask = mean_att > threshold
+  edge_index = data_edge_index[:, mask]
+  kept = mean_att[mask]
+  index = edge_index[opt['attention_norm_idx']]
+  sums = scatter_add(kept, index, num_nodes)[index]
+  return edge_index, kept / (sums + 1e-16)
+
+
 def laplacian_weights(opt: dict, edge_weight: Optional[Tensor], attention_weights: Optional[Tensor]) -> Tensor:
   """Which per-edge weight LaplacianODEFunc.sparse_multiply uses, by block name; :28-36."""
   if opt['block'] in ['attention']:

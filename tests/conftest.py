@@ -25,5 +25,9 @@ def pytest_collection_modifyitems(config, items):
 
 @pytest.fixture(scope='session')
 def golden():
-  path = os.path.join(ROOT, 'tests', 'golden', 'golden_v1.pt')
-  return torch.load(path, map_location='cpu', weights_only=False)
+  cases = {}
+  for name in ('golden_v1.pt', 'golden_v2.pt'):   # v2: GAT scorer + hard-attention block (make_golden_v2.py)
+    part = torch.load(os.path.join(ROOT, 'tests', 'golden', name), map_location='cpu', weights_only=False)
+    assert not set(part) & set(cases)
+    cases.update(part)
+  return cases

@@ -67,6 +67,20 @@ def test_blocks(golden):
     C.assert_close(z, c['outputs']['z'], 1e-5, name + ' z')
 
 
+def test_hard_attention_edge_selection(golden):
+  """HardAttODEblock (reference src/block_transformer_hard_attention.py:49-68): the kept edge set is reproduced
+  exactly, the renormalised weights to rounding; training keeps ~att_samp_pct of the edges, eval keeps all."""
+  names = [n for n in _names(golden, 'block') if golden[n]['opt']['block'] == 'hard_attention']
+  assert len(names) == 6
+  for name in names:
+    c = golden[name]
+    _, _, _, (ei, _), extra = C.oracle_block(c, want_extra=True)
+    assert torch.equal(ei, c['outputs']['odefunc_edge_index']), name
+    C.assert_close(extra['attention_weights'], c['outputs']['attention_weights'], ORACLE_RTOL, name + ' weights')
+    kept = ei.shape[1] / c['outputs']['odefunc_edge_weight'].shape[0]
+    assert (abs(kept - c['opt']['att_samp_pct']) < 0.02) if c['inputs']['train'] else kept == 1.0, name
+
+
 def test_blocks_fp64_arbiter(golden):
   for name in _names(golden, 'block'):
     c = golden[name]

@@ -100,7 +100,7 @@ def test_host_dopri5_matches_oracle_on_golden_blocks(golden, monkeypatch):
     # (ratio ~1e-5), so two correct implementations may pick step sizes a few % apart and then land on different
     # dense-output points; the solution they return agrees to the solver's own accuracy, not to 1e-5.  Judge both
     # against a tight fp64 integration of the same ODE.
-    exact = C.exact_block_solution(c)
+    exact = C.exact_block_solution(c, name)
     ref_err = C.rel_err(c['outputs']['z'], exact)
     got_err = C.rel_err(out[1], exact)
     assert got_err <= 1.5 * ref_err + 1e-5, '%s: host dopri5 %.2e vs exact, reference %.2e' % (name, got_err, ref_err)
@@ -119,3 +119,31 @@ def test_host_dopri5_interior_times_and_rejections(monkeypatch):
   out, solver, func = run_host_dopri5(f, y0, t, 1e-6, 1e-8, monkeypatch)
   assert stats.rejected > 0 and solver.attempts == stats.accepted + stats.rejected
   C.assert_close(out, want, 5e-6, 'dense output')
+
+
+def test_early_stop_device_scoring_matches_host_logic():
+  """The sync-free scorer (running best kept in a device tensor, one read at the end) must reproduce the reference's
+  per-step host logic (src/early_stop_solver.py:203-218, :172-176): same accuracies as python int/int, strict '>'."""
+  from graph_neural_pde_b200.early_stop_solver import EarlyStopRK4
+
+  class Split:
+    pass
+
+  torch.manual_seed(0)
+  n, classes, d = 200, 5, 16
+  for dataset, yshape in (('Cora', (n,)), ('ogbn-arxiv', (n, 1))):
+    data = Split()
+    data.y = torch.randint(0, classes, yshape)
+    r = torch.rand(n)
+    data.train_mask, data.val_mask, data.test_mask = r < 0.3, (r >= 0.3) & (r < 0.6), r >= 0.6
+    solver = EarlyStopRK4(None, None, 1e-3, 1e-3, {'dataset': dataset, 'max_test_steps': 100}, step_size=1.0)
+    solver.data, solver.m2_weight, solver.m2_bias = data, torch.randn(classes, d), torch.randn(classes)
+    best = (0, 0, 0, 0)
+    for step in range(12):
+      y = torch.randn(n, d)
+      accs = solver.evaluate(y)            # the reference's host path
+      if accs[1] > best[1]:
+        best = (accs[0], accs[1], accs[2], float(step + 1))
+      solver._score(y, step + 1)
+    solver._publish()
+    assert best == (solver.best_train, solver.best_val, solver.best_test, solver.best_time), dataset
