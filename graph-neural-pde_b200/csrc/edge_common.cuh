@@ -135,6 +135,7 @@ __device__ __forceinline__ void st_stream4_hint(float* p, float4 v, uint64_t pol
                : "memory");
 }
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
 // ---- segmented all-reduce over contiguous lane segments [lo, hi): every lane gets its own segment's value ----
 __device__ __forceinline__ float seg_max(float v, int lane, int lo, int hi) {
@@ -144,6 +145,15 @@ __device__ __forceinline__ float seg_max(float v, int lane, int lo, int hi) {
     if (lane + o < hi) v = fmaxf(v, t);
   }
   return __shfl_sync(kFull, v, lo);
+}
+// the same maximum in ONE warp instruction: redux.sync over the segment's member mask on the order-preserving integer
+// image of the float (every lane of a segment passes the same mask; lanes outside any segment pass their own bit)
+__device__ __forceinline__ unsigned seg_mask(int lane, int lo, int hi, bool member) {
+  const unsigned upto_hi = hi >= 32 ? 0xffffffffu : ((1u << hi) - 1u);
+  return member ? (upto_hi & ~((1u << lo) - 1u)) : (1u << lane);
+}
+__device__ __forceinline__ float seg_max_redux(float v, unsigned mask) {
+  return ordered_to_float(__reduce_max_sync(mask, float_to_ordered(v)));
 }
 __device__ __forceinline__ float seg_sum(float v, int lane, int lo, int hi) {
 #pragma unroll

@@ -25,11 +25,17 @@ namespace grand {
 
 constexpr int kRhsThreads = 128;  // 4 warps per block
 constexpr int kRhsWarps = kRhsThreads / kWarp;
+// Register staging: neighbour rows in flight per warp and resident blocks per SM.  Measured on ogbn-arxiv (B200,
+// profiles/r01f_*): batch 8 x 8 blocks (32 warps/SM, 64 regs) 337 us, batch 4 x 12 blocks (48 warps/SM, 42 regs) 327 us,
+// batch 4 x 10 blocks 332 us, batch 8 x 6 blocks 392 us -- more resident windows beat deeper batches.
 #ifndef GRAND_DIRECT_BATCH
-#define GRAND_DIRECT_BATCH 8
+#define GRAND_DIRECT_BATCH 4
 #endif
 #ifndef GRAND_DIRECT_MINBLOCKS
-#define GRAND_DIRECT_MINBLOCKS 8
+#define GRAND_DIRECT_MINBLOCKS 12
+#endif
+#ifndef GRAND_EPI_PREFETCH
+#define GRAND_EPI_PREFETCH 0   // measured: 350 us with, 337 us without (the prefetched lines displace gather rows in L1)
 #endif
 constexpr int kDirectBatch = GRAND_DIRECT_BATCH;   // STAGE_DIRECT: neighbour rows in flight per warp (divided by R)
 
@@ -119,6 +125,27 @@ split_row_merge_kernel(GraphView g, int H, const float* __restrict__ split_stats
   }
 }
 
+// ---- epilogue operands of one row towards L1 while the row's neighbours are being gathered ------------------------------
+// A row's epilogue reads x_i, x0_i and the stage-combine terms (up to 6 x 512 B for rk4 on ogbn-arxiv).  Issued as plain
+// loads after the gather they cost one exposed round trip per row (ncu: ~25 % of the stall samples of the kernel sat on
+// those loads).  One prefetch instruction per lane -- lane -> (tensor, 128-byte line) -- starts all of them before the
+// gather loop at no register cost; the loads in finish_row then hit L1.  MEASURED SLOWER (see GRAND_EPI_PREFETCH): kept
+// as a build switch for the record, off by default.
+__device__ __forceinline__ void prefetch_row_operands(const RhsArgs& A, int row, int lane) {
+  const int row_bytes = A.d * (int)sizeof(float);
+  const int lines = (row_bytes + 127) >> 7;
+  const int n_tensors = 1 + (A.ep.x0 != nullptr ? 1 : 0) + (A.ep.y_out != nullptr ? A.ep.n_terms : 0);
+  const size_t off = (size_t)row * row_bytes;
+  for (int idx = lane; idx < n_tensors * lines; idx += kWarp) {
+    const int ts = idx / lines, ln = idx - ts * lines;
+    const float* basep;
+    if (ts == 0) basep = A.x;
+    else if (A.ep.x0 != nullptr && ts == 1) basep = A.ep.x0;
+    else basep = A.ep.term[ts - 1 - (A.ep.x0 != nullptr ? 1 : 0)];
+    prefetch_l1(reinterpret_cast<const char*>(basep) + off + (size_t)ln * 128);
+  }
+}
+
 // ---- epilogue: residual + RK stage combine for one finished row -----------------------------------------------------
 template <int VEC, int R>
 __device__ __forceinline__ void finish_row(const RhsArgs& A, int row, int lane, float alpha, float beta,
@@ -135,7 +162,11 @@ __device__ __forceinline__ void finish_row(const RhsArgs& A, int row, int lane, 
       float4 s0 = make_float4(0.f, 0.f, 0.f, 0.f);
       if (A.ep.x0 != nullptr) s0 = ld_stream4_hint(A.ep.x0 + base + c, pol_stream);
       constexpr int kTB = 4;   // stage-combine terms are loaded four at a time (rk4 needs <= 4, dopri5 up to 7)
+      // every element initialised: a conditionally-written array ends up in LOCAL memory (ncu: more local than global
+      // load requests in this kernel before the change), zero-initialised it stays in 16 registers
       float4 tv[kTB];
+#pragma unroll
+      for (int t = 0; t < kTB; ++t) tv[t] = make_float4(0.f, 0.f, 0.f, 0.f);
       if (A.ep.y_out != nullptr) {
 #pragma unroll
         for (int t = 0; t < kTB; ++t)
@@ -300,20 +331,59 @@ rhs_window_kernel(const __grid_constant__ RhsArgs A) {
     const float* kj = A.k + (size_t)j * A.a.ad_eff;
     const float ew = (valid && A.a.edge_weight_csr != nullptr) ? __ldg(A.a.edge_weight_csr + beg + lane) : 1.f;
     const int H = A.a.heads;
-    for (int h = 0; h < H; ++h) {
-      float s = -INFINITY;
-      if (valid) s = fused_score(A.a, qi + h * A.a.dk, kj + h * A.a.dk, vec4) * ew;   // ew: reweight_attention :208-209
-      float m, l, e;
-      if (split < 0) {
-        m = seg_max(s, lane, lo, hi);
-        e = valid ? expf(s - m) : 0.f;
-        l = seg_sum(e, lane, lo, hi);
-      } else {
-        m = __ldg(A.row_stats + ((size_t)split * H + h) * 2 + 0);
-        l = __ldg(A.row_stats + ((size_t)split * H + h) * 2 + 1);
-        e = valid ? expf(s - m) : 0.f;
+    const unsigned smask = seg_mask(lane, lo, hi, valid && split < 0);
+    if (A.a.dk == 4 && vec4 && H <= 4) {
+      // d_k = 4 (ogbn-arxiv: ad 16, 4 heads): a head is ONE float4 of the Q / K row.  All 2 H loads are issued before
+      // the first score so the window pays one round trip for them, not one per head.
+      float4 qv[4], kv[4];
+#pragma unroll
+      for (int h = 0; h < 4; ++h) {
+        qv[h] = make_float4(0.f, 0.f, 0.f, 0.f);
+        kv[h] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (h < H && valid) {
+          qv[h] = ldg4(qi + 4 * h);
+          kv[h] = ldg4(kj + 4 * h);
+        }
       }
-      ab += e / (l + 1e-16f);
+#pragma unroll
+      for (int h = 0; h < 4; ++h) {
+        if (h < H) {
+          float s = -INFINITY;
+          if (valid) {
+            float t = 0.f;
+            t = fmaf(qv[h].x, kv[h].x, t); t = fmaf(qv[h].y, kv[h].y, t);
+            t = fmaf(qv[h].z, kv[h].z, t); t = fmaf(qv[h].w, kv[h].w, t);
+            s = (t * 0.5f) * ew;              // / sqrt(4): exact; ew: reweight_attention :208-209
+          }
+          float m, l, e;
+          if (split < 0) {
+            m = seg_max_redux(s, smask);
+            e = valid ? expf(s - m) : 0.f;
+            l = seg_sum(e, lane, lo, hi);
+          } else {
+            m = __ldg(A.row_stats + ((size_t)split * H + h) * 2 + 0);
+            l = __ldg(A.row_stats + ((size_t)split * H + h) * 2 + 1);
+            e = valid ? expf(s - m) : 0.f;
+          }
+          ab += e / (l + 1e-16f);
+        }
+      }
+    } else {
+      for (int h = 0; h < H; ++h) {
+        float s = -INFINITY;
+        if (valid) s = fused_score(A.a, qi + h * A.a.dk, kj + h * A.a.dk, vec4) * ew;
+        float m, l, e;
+        if (split < 0) {
+          m = seg_max_redux(s, smask);
+          e = valid ? expf(s - m) : 0.f;
+          l = seg_sum(e, lane, lo, hi);
+        } else {
+          m = __ldg(A.row_stats + ((size_t)split * H + h) * 2 + 0);
+          l = __ldg(A.row_stats + ((size_t)split * H + h) * 2 + 1);
+          e = valid ? expf(s - m) : 0.f;
+        }
+        ab += e / (l + 1e-16f);
+      }
     }
     ab = ab / (float)H;
   }
@@ -421,6 +491,7 @@ rhs_window_kernel(const __grid_constant__ RhsArgs A) {
     for (int r = 0; r < R; ++r)
 #pragma unroll
       for (int v = 0; v < VEC; ++v) acc[r][v] = 0.f;
+    if (GRAND_EPI_PREFETCH && split < 0) prefetch_row_operands(A, row0 + kr, lane);
 
     if (STAGE == STAGE_CPASYNC || STAGE == STAGE_BULK) {
       if (full) {
