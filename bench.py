@@ -182,7 +182,7 @@ def run_reference(args, rank, world):
     'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
     'gpu_launches': 0,
   }
-  print(json.dumps(line), flush=True)
+  emit(line)
 
 
 def workload_config(name, opt, n, e, extra=None):
@@ -437,7 +437,7 @@ def run_native_single(args):
                      'sample': '2 timed samples of 1 rk4 step = 4 RHS evals of the oracle (torch CPU ops)',
                      'ms_per_rhs_eval': None if args.skip_cpu else sec * 1e3 / 4},
   }
-  print(json.dumps(line), flush=True)
+  emit(line)
 
 
 def run_native_multi(args, rank, world):
@@ -552,12 +552,34 @@ def run_native_multi(args, rank, world):
                    'nvlink_bytes_per_rhs_eval': halo_bytes,
                    'nvlink_time_floor_us_per_eval': max(s['halo_rows'] for s in summaries) * d * 4 / 770e9 * 1e6},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
   dist.barrier()
   dist.destroy_process_group()
 
 
+_RESULT_FD = None
+
+
+def quiet_stdout():
+  """Everything libraries print on stdout (NCCL prints its version line there under NCCL_DEBUG=VERSION) is sent to
+  stderr, so that the ONE JSON line emit() writes is the only thing on the real stdout."""
+  global _RESULT_FD
+  sys.stdout.flush()
+  _RESULT_FD = os.dup(1)
+  os.dup2(2, 1)
+
+
+def emit(line):
+  text = json.dumps(line) + '\n'
+  if _RESULT_FD is None:
+    sys.stdout.write(text)
+    sys.stdout.flush()
+  else:
+    os.write(_RESULT_FD, text.encode())
+
+
 def main():
+  quiet_stdout()
   ap = argparse.ArgumentParser()
   ap.add_argument('--gpus', type=int, default=1)
   ap.add_argument('--steps', type=int, default=20)

@@ -200,3 +200,34 @@ def test_nfe_guard_counts_like_the_reference():
   assert f.nfe == 6
   with pytest.raises(U.MaxNFEException):
     f._bump_nfe()
+
+
+def test_hard_attention_selection_host_logic(golden, monkeypatch):
+  """HardAttODEblock.select_edges (quantile threshold, optional flux weighting, mask, per-node renormalisation) on the
+  CPU with the attention values taken from the oracle: the kept edge set must equal the reference's exactly and the
+  renormalised weights to rounding (reference src/block_transformer_hard_attention.py:43-68)."""
+  from graph_neural_pde_b200.block_transformer_hard_attention import HardAttODEblock
+  dev = torch.device('cpu')
+  names = [n for n, c in golden.items() if c['kind'] == 'block' and c['opt']['block'] == 'hard_attention']
+  assert len(names) == 6
+  for name in names:
+    c = golden[name]
+    opt = copy.deepcopy(c['opt'])
+    inp = c['inputs']
+    data = Data(x=inp['x'], edge_index=inp['edge_index'], edge_attr=inp['edge_attr'], num_nodes=inp['num_nodes'])
+    block = HardAttODEblock(set_function(opt), (), opt, data, dev, t=torch.tensor([0, opt['time']]))
+    block.load_state_dict(c['state_dict'], strict=True)
+    block.train(bool(inp['train']))
+    S = c['state_dict']
+    if opt['function'] == 'laplacian':
+      att, _ = O.attention_forward(inp['x'], block.data_edge_index, C.sub_state(S, 'multihead_att_layer.'), opt,
+                                   block.odefunc.edge_weight)
+    else:
+      att, _ = O.attention_forward(inp['x'], block.data_edge_index, C.sub_state(S, 'odefunc.multihead_att_layer.'), opt,
+                                   None)
+    monkeypatch.setattr(block, 'get_attention_weights', lambda x, att=att: att)
+    edge_index, weights = block.select_edges(inp['x'])
+    assert torch.equal(edge_index, c['outputs']['odefunc_edge_index']), name
+    C.assert_close(weights, c['outputs']['attention_weights'], 2e-6, name)
+    block._share(edge_index, weights)
+    assert block.reg_odefunc.odefunc.attention_weights is weights and block.odefunc.edge_index is edge_index
