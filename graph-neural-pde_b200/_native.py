@@ -78,6 +78,7 @@ SIGNATURES = {
   'grand_lincomb': (C.c_int, [C.c_int64, C.c_int32, C.POINTER(C.c_void_p), c_float_p, _P, _P]),
   'grand_error_sumsq': (C.c_int, [C.c_int64, C.c_int32, C.POINTER(C.c_void_p), c_float_p, _P, _P, C.c_float,
                                    C.c_float, _P, _P]),
+  'grand_plan_pack_rows': (C.c_int64, [_P, C.c_int64, C.c_int32, C.c_int32, _P, _P]),
 }
 
 

@@ -21,33 +21,16 @@ from . import _native as N
 
 def pack_short_rows(deg, tile, max_rows):
   """Greedy packing of consecutive short rows into windows: -> (first row, row count) per window (int64 arrays).
-  One pass over the degree array; rows with more than `tile` edges are skipped (they are chunked separately) and
-  close the current window, because a window covers a contiguous CSR range."""
+  The pass is sequential by nature and runs in the native library (grand_plan_pack_rows, csrc/plan_host.cu: plain host
+  code, so it also works on a machine without a GPU); rows with more than `tile` edges are skipped (they are chunked
+  separately) and close the current window, because a window covers a contiguous CSR range."""
+  deg = np.ascontiguousarray(deg, dtype=np.int64)
   n = len(deg)
-  first = np.empty(n, dtype=np.int64)
-  count = np.empty(n, dtype=np.int64)
-  w = 0
-  start, edges, rows = -1, 0, 0
-  d = deg.tolist()
-  for r in range(n):
-    dr = d[r]
-    if dr > tile:
-      if rows:
-        first[w], count[w] = start, rows
-        w += 1
-        rows = 0
-      continue
-    if rows and (edges + dr > tile or rows == max_rows):
-      first[w], count[w] = start, rows
-      w += 1
-      rows = 0
-    if rows == 0:
-      start, edges = r, 0
-    edges += dr
-    rows += 1
-  if rows:
-    first[w], count[w] = start, rows
-    w += 1
+  first = np.empty(max(n, 1), dtype=np.int64)
+  count = np.empty(max(n, 1), dtype=np.int64)
+  w = N.lib().grand_plan_pack_rows(deg.ctypes.data, n, int(tile), int(max_rows), first.ctypes.data, count.ctypes.data)
+  if w < 0:
+    raise N.GrandError('grand_plan_pack_rows failed (%d): bad degrees / tile / max_rows' % w)
   return first[:w].copy(), count[:w].copy()
 
 

@@ -213,6 +213,13 @@ int grand_lincomb(int64_t n, int32_t n_terms, const float* const* term, const fl
 int grand_error_sumsq(int64_t n, int32_t n_terms, const float* const* k, const float* coef, const float* y0,
                       const float* y1, float atol, float rtol, double* sumsq, void* stream);
 
+/* HOST function (plain CPU code, no CUDA call): the sequential step of building a grand_graph -- greedy packing of
+ * consecutive rows with <= tile in-edges into windows of <= tile edges and <= max_rows (<= GRAND_MAX_PACKED_ROWS) rows;
+ * rows with more edges are skipped (they are cut into chunks) and close the current window.  deg[n_rows] are the row
+ * degrees; first[w] / count[w] (capacity n_rows each) receive the first row and the row count of window w.  Returns the
+ * number of windows or a negative error code.  The reference has no counterpart (torch_sparse.spmm takes raw COO). */
+int64_t grand_plan_pack_rows(const int64_t* deg, int64_t n_rows, int32_t tile, int32_t max_rows, int64_t* first,
+                             int64_t* count);
 #ifdef __cplusplus
 }
 #endif

@@ -231,3 +231,40 @@ def test_hard_attention_selection_host_logic(golden, monkeypatch):
     C.assert_close(weights, c['outputs']['attention_weights'], 2e-6, name)
     block._share(edge_index, weights)
     assert block.reg_odefunc.odefunc.attention_weights is weights and block.odefunc.edge_index is edge_index
+
+
+def _pack_rows_python(deg, tile, max_rows):
+  """Straightforward restatement of the packing rule, the checker for the native grand_plan_pack_rows."""
+  first, count = [], []
+  start, edges, rows = -1, 0, 0
+  for r, dr in enumerate(deg):
+    if dr > tile:
+      if rows:
+        first.append(start); count.append(rows); rows = 0
+      continue
+    if rows and (edges + dr > tile or rows == max_rows):
+      first.append(start); count.append(rows); rows = 0
+    if rows == 0:
+      start, edges = r, 0
+    edges += dr
+    rows += 1
+  if rows:
+    first.append(start); count.append(rows)
+  return first, count
+
+
+def test_native_row_packing_matches_python_rule():
+  import numpy as np
+  from graph_neural_pde_b200.graph_plan import pack_short_rows
+  rng = np.random.default_rng(0)
+  cases = [np.zeros(0, dtype=np.int64), np.zeros(5, dtype=np.int64), np.full(40, 32), np.full(7, 33),
+           rng.integers(0, 50, size=1000), rng.integers(0, 6, size=3000), np.array([0, 0, 40, 0, 31, 1, 1, 100, 2])]
+  for deg in cases:
+    for tile, max_rows in [(32, 8), (32, 1), (16, 4)]:
+      first, count = pack_short_rows(deg, tile, max_rows)
+      want_first, want_count = _pack_rows_python(deg.tolist(), tile, max_rows)
+      assert first.tolist() == want_first and count.tolist() == want_count
+      covered = sum(count.tolist())
+      assert covered == int((np.asarray(deg) <= tile).sum())          # every short row in exactly one window
+  with pytest.raises(Exception):
+    pack_short_rows(np.array([-1, 2]), 32, 8)
