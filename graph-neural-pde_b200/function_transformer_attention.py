@@ -17,6 +17,11 @@ from .graph_plan import GraphPlan
 from .utils import add_remaining_self_loops
 
 
+_MIX_FEATURES = ('mix_features=True is not built: the reference itself cannot run it for this function (its forward passes '
+                 'the layer\'s (v, prods) tuple to multiply_attention, whose v.shape raises -- reference '
+                 'src/function_transformer_attention.py:43-44, :29), so there is no behaviour to reproduce')
+
+
 class SpGraphTransAttentionLayer(nn.Module):
   """Parameters, their names and their initialisation follow the reference (:66-126): Q, K, V, Wout Linear layers
   with weight = 1e-5 and default bias; exp_kernel scalars; the beltrami + exp_kernel variant owns Qx/Kx/Vx/Qp/Kp/Vp.
@@ -112,8 +117,9 @@ class SpGraphTransAttentionLayer(nn.Module):
     the V projection is dead on the mix_features=False path and is not computed."""
     N.require_cuda(x, 'x')
     if x.requires_grad and torch.is_grad_enabled():
-      raise NotImplementedError('grand_b200: the attention backward kernels are not built yet (SURVEY.md 8(f).1); '
-                                'call under torch.no_grad()')
+      raise NotImplementedError('grand_b200: the standalone attention layer is forward-only (gradients flow through '
+                                'ODEFuncTransformerAtt.forward, not through frozen attention weights); call under '
+                                'torch.no_grad()')
     engine = engine if engine is not None else self._engine_for(x, edge)
     attention, prods, _ = engine.attention_weights(self.spec(engine), x.contiguous())
     return attention, (None, prods)
@@ -144,7 +150,7 @@ class ODEFuncTransformerAtt(ODEFunc):
   def native_description(self, engine):
     """(attention spec, None): what the solvers hand to the kernels instead of calling forward per stage."""
     if self.opt['mix_features']:
-      raise NotImplementedError('mix_features=True is outside the built hot path (SURVEY.md 8(f).4)')
+      raise NotImplementedError(_MIX_FEATURES)
     return self.multihead_att_layer.spec(engine), None
 
   def stage_x0(self, engine):
@@ -157,8 +163,7 @@ class ODEFuncTransformerAtt(ODEFunc):
 
   def forward(self, t, x):  # t is needed when called by the integrator
     if self.opt['mix_features']:
-      raise NotImplementedError('mix_features=True (per-head value path, reference :27-32) is outside the built '
-                                'hot path (SURVEY.md 8(f).4)')
+      raise NotImplementedError(_MIX_FEATURES)
     self._bump_nfe()
     N.require_cuda(x, 'x')
     if needs_grad(self, x):
