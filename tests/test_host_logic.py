@@ -268,3 +268,29 @@ def test_native_row_packing_matches_python_rule():
       assert covered == int((np.asarray(deg) <= tile).sum())          # every short row in exactly one window
   with pytest.raises(Exception):
     pack_short_rows(np.array([-1, 2]), 32, 8)
+
+
+def test_model_shell_matches_reference(golden):
+  """Encoder / decoder either side of the ODE block (reference src/GNN.py:17-77, src/base_classes.py:98-131), eval
+  mode, every shell option: `embed` must reproduce the tensor the reference hands to its block and `readout` the
+  reference's logits from the reference's block output (tests/golden/make_golden_v3.py recorded both)."""
+  from graph_neural_pde_b200.models import GNN
+  from graph_neural_pde_b200.utils import DummyDataset
+  names = sorted(k for k, v in golden.items() if v['kind'] == 'model_shell')
+  assert len(names) == 8
+  for name in names:
+    c = golden[name]
+    opt, inp, out = copy.deepcopy(c['opt']), c['inputs'], c['outputs']
+    # the reference constructor rewrote hidden_dim in place (beltrami / use_labels); undo it for a fresh construction
+    if opt['use_labels']:
+      opt['hidden_dim'] -= inp['num_classes']
+    data = Data(x=inp['x'][:, :inp['num_features']], edge_index=inp['edge_index'], edge_attr=None,
+                num_nodes=inp['num_nodes'])
+    model = GNN(opt, DummyDataset(data, inp['num_classes']), torch.device('cpu'))
+    model.load_state_dict(c['state_dict'], strict=True)
+    model.eval()
+    with torch.no_grad():
+      x0 = model.embed(inp['x'], inp['pos_encoding'])
+      C.assert_close(x0, out['block_in'], 2e-6, name + ' embed')
+      logits = model.readout(out['block_out'], x0.shape[1])
+      C.assert_close(logits, out['logits'], 2e-6, name + ' readout')
