@@ -24,7 +24,7 @@ def _graph(n=400, m=1800):
 
 def test_partition_invariants():
   ei, n = _graph()
-  for world in (1, 2, 3, 5):
+  for world in (1, 2, 3, 5, 8):     # 8 = the node the scaling run uses
     parts = [Partition(ei, n, world, r) for r in range(world)]
     assert parts[0].bounds[0] == 0 and parts[0].bounds[-1] == n
     assert sum(p.n_own for p in parts) == n and sum(p.n_local_edges for p in parts) == ei.shape[1]
