@@ -83,7 +83,8 @@ def main(cmd_opt):
       opt = {**opt, **{k: v for k, v in baseline_opt(key).items() if k in (
         'function', 'block', 'hidden_dim', 'attention_dim', 'heads', 'method', 'time', 'step_size', 'tol_scale',
         'add_source', 'max_nfe')}}
-  for flag in ('rewire_KNN', 'fa_layer', 'beltrami', 'cgnn', 'use_labels', 'edge_sampling'):
+  for flag in ('rewire_KNN', 'fa_layer', 'beltrami', 'cgnn', 'use_labels', 'edge_sampling', 'KNN_online',
+               'edge_sampling_online', 'symmetric_attention'):
     if opt.get(flag):
       raise NotImplementedError('--%s is outside the grand_b200 hot-path scope (SURVEY.md section 8)' % flag)
   if opt['method'] is None:
@@ -118,6 +119,19 @@ def main(cmd_opt):
   print('best val accuracy {:03f} with test accuracy {:03f} at epoch {:d} and best time {:03f}'.format(
     val_acc, test_acc, best_epoch, best_time))
   return train_acc, val_acc, test_acc
+
+
+_COMPAT_VALUE_FLAGS = {
+  'KNN_online_reps': 4, 'KNN_space': 'pos_distance', 'M_nodes': 64, 'edge_sampling_T': 'T0', 'edge_sampling_add': 0.64,
+  'edge_sampling_add_type': 'importance', 'edge_sampling_epoch': 5, 'edge_sampling_online_reps': 4,
+  'edge_sampling_rmv': 0.32, 'edge_sampling_space': 'attention', 'fa_layer_edge_sampling_rmv': 0.8,
+  'gdc_avg_degree': 64, 'gdc_k': 64, 'gdc_method': 'ppr', 'gdc_sparsification': 'topk', 'gdc_threshold': 0.0001,
+  'heat_time': 3.0, 'new_edges': 'random', 'pos_dist_quantile': 0.001, 'pos_enc_orientation': 'row', 'ppr_alpha': 0.05,
+  'rewire_KNN_T': 'T0', 'rewire_KNN_epoch': 5, 'rewire_KNN_k': 64, 'rw_addD': 0.02, 'rw_rmvR': 0.02, 'sparsify': 'S_hat',
+  'threshold_type': 'topk_adj',
+}
+_COMPAT_SWITCHES = ('KNN_online', 'edge_sampling_online', 'edge_sampling_sym', 'exact', 'pos_enc_csv', 'rewire_KNN_sym',
+                    'symmetric_attention')
 
 
 def build_parser():
@@ -190,6 +204,16 @@ def build_parser():
   a('--feat_hidden_dim', type=int, default=64)
   a('--pos_enc_hidden_dim', type=int, default=32)
   a('--gpu', type=int, default=0)
+  # hard-attention block (reference src/run_GNN.py:388-391)
+  a('--att_samp_pct', type=float, default=1)
+  a('--use_flux', dest='use_flux', action='store_true')
+  # flags of subsystems outside the hot path (rewiring, GDC, edge sampling, KNN, positional-encoding files): parsed with
+  # the reference's types and defaults so that its command lines and opt dictionaries carry over; the features
+  # themselves are refused where they would act (main)
+  for name, default in _COMPAT_VALUE_FLAGS.items():
+    a('--' + name, type=type(default), default=default)
+  for name in _COMPAT_SWITCHES:
+    a('--' + name, action='store_true')
   # additions of this repository
   a('--best_params', action='store_true', help='overlay the hot-path keys of the BASELINE config for the dataset')
   a('--quiet', action='store_true')

@@ -123,6 +123,7 @@ def default_opt(**overrides):
     'jacobian_norm2': None, 'total_deriv': None, 'kinetic_energy': None, 'directional_penalty': None,
     'not_lcc': True, 'rewiring': None, 'rewire_KNN': False, 'fa_layer': False, 'beltrami': False,
     'feat_hidden_dim': 64, 'pos_enc_hidden_dim': 32, 'pos_enc_type': 'DW64', 'edge_sampling': False, 'gpu': 0,
+    'att_samp_pct': 1, 'use_flux': False,
   }
   opt.update(overrides)
   return opt

@@ -294,3 +294,26 @@ def test_model_shell_matches_reference(golden):
       C.assert_close(x0, out['block_in'], 2e-6, name + ' embed')
       logits = model.readout(out['block_out'], x0.shape[1])
       C.assert_close(logits, out['logits'], 2e-6, name + ' readout')
+
+
+def test_cli_flags_and_defaults_match_reference():
+  """Every flag of the reference's run_GNN.py (src/run_GNN.py:283-436, recorded by tests/golden/make_cli_defaults.py)
+  parses here with the same default and type, so reference command lines and opt dictionaries carry over."""
+  import importlib
+  import json
+  import os
+  parser = importlib.import_module('graph_neural_pde_b200.run_GNN').build_parser()
+  mine = {o[2:]: a for a in parser._actions for o in a.option_strings if o.startswith('--')}
+  path = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'cli_defaults.json')
+  ref = json.load(open(path))
+  assert len(ref) >= 100
+  for name, spec in ref.items():
+    assert name in mine, 'flag --%s missing' % name
+    if spec['default'] != '<expr>':
+      assert mine[name].default == spec['default'], '--%s default %r vs %r' % (name, mine[name].default, spec['default'])
+    if 'type' in spec:
+      assert mine[name].type.__name__ == spec['type'], '--%s type' % name
+    if 'dest' in spec:
+      assert mine[name].dest == spec['dest'], '--%s dest' % name
+  opt = vars(parser.parse_args(['--block', 'hard_attention', '--att_samp_pct', '0.5', '--use_flux']))
+  assert opt['att_samp_pct'] == 0.5 and opt['use_flux'] is True
