@@ -317,3 +317,31 @@ def test_cli_flags_and_defaults_match_reference():
       assert mine[name].dest == spec['dest'], '--%s dest' % name
   opt = vars(parser.parse_args(['--block', 'hard_attention', '--att_samp_pct', '0.5', '--use_flux']))
   assert opt['att_samp_pct'] == 0.5 and opt['use_flux'] is True
+
+
+def test_reference_best_params_overlay():
+  """`--best_params reference` = the reference's {**cmd_opt, **best_params_dict[dataset]} + merge_cmd_args
+  (src/run_GNN.py:188-221): table values win, except the few command-line values the reference lets through."""
+  import importlib
+  mod = importlib.import_module('graph_neural_pde_b200.run_GNN')
+  parse = lambda argv: vars(mod.build_parser().parse_args(argv))
+  opt = mod.reference_best_params(parse(['--dataset', 'ogbn-arxiv', '--best_params', 'reference']))
+  got = (opt['function'], opt['block'], opt['method'], opt['adjoint'], opt['adjoint_method'])
+  # reference quirk kept: --block / --function have non-None CLI defaults, so merge_cmd_args lets the DEFAULT
+  # 'constant' override the table's 'hard_attention' unless --block is given
+  assert got == ('laplacian', 'constant', 'dopri5', True, 'rk4')
+  assert mod.reference_best_params(parse(['--dataset', 'ogbn-arxiv', '--block', 'hard_attention']))['block'] == \
+      'hard_attention'
+  assert opt['hidden_dim'] == 162 and opt['heads'] == 2 and abs(opt['att_samp_pct'] - 0.8105268910037231) < 1e-12
+  opt = mod.reference_best_params(parse(['--dataset', 'Cora', '--time', '3', '--method', 'rk4', '--step_size', '0.5']))
+  assert (opt['block'], opt['time'], opt['method'], opt['step_size']) == ('constant', 3.0, 'rk4', 0.5)
+  assert opt['hidden_dim'] == 80 and opt['square_plus'] is True          # table wins over the CLI default
+  assert mod.reference_best_params(parse(['--dataset', 'Nowhere']))['hidden_dim'] == 16
+  # and against the reference's own merge_cmd_args, exec'd from its source by tests/golden/make_cli_defaults.py
+  import json
+  import os
+  path = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'cli_overlay_cases.json')
+  for case in json.load(open(path)):
+    got = mod.reference_best_params(parse(case['argv']))
+    for key, want in case['opt'].items():
+      assert got[key] == want, '%s: %s = %r, reference %r' % (case['argv'], key, got[key], want)
