@@ -34,6 +34,23 @@ constexpr int kRhsWarps = kRhsThreads / kWarp;
 #ifndef GRAND_DIRECT_MINBLOCKS
 #define GRAND_DIRECT_MINBLOCKS 12
 #endif
+// A/B build switches for the next measurements (tools/ab_stage.sh builds and times the variants); the defaults below
+// are the measured-best configuration and compile to exactly the validated kernel:
+//   GRAND_SEGMAX_SHUFFLE=1     segment max by the 11-instruction shuffle reduction instead of redux.sync (ncu: the
+//                              non-uniform-mask redux expands to ~28 instructions per call)
+//   GRAND_EPI_TERMS_BATCH=2    stage-combine terms loaded two at a time (8 instead of 16 registers in the epilogue; the
+//                              40-register build spills there)
+#ifndef GRAND_SEGMAX_SHUFFLE
+#define GRAND_SEGMAX_SHUFFLE 0
+#endif
+#if GRAND_SEGMAX_SHUFFLE
+#define GRAND_SEG_MAX(s) seg_max(s, lane, lo, hi)
+#else
+#define GRAND_SEG_MAX(s) seg_max_redux(s, smask)
+#endif
+#ifndef GRAND_EPI_TERMS_BATCH
+#define GRAND_EPI_TERMS_BATCH 4
+#endif
 #ifndef GRAND_EPI_PREFETCH
 #define GRAND_EPI_PREFETCH 0   // measured: 350 us with, 337 us without (the prefetched lines displace gather rows in L1)
 #endif
@@ -161,7 +178,7 @@ __device__ __forceinline__ void finish_row(const RhsArgs& A, int row, int lane, 
       const float4 xi = ldg4(A.x + base + c);
       float4 s0 = make_float4(0.f, 0.f, 0.f, 0.f);
       if (A.ep.x0 != nullptr) s0 = ld_stream4_hint(A.ep.x0 + base + c, pol_stream);
-      constexpr int kTB = 4;   // stage-combine terms are loaded four at a time (rk4 needs <= 4, dopri5 up to 7)
+      constexpr int kTB = GRAND_EPI_TERMS_BATCH;   // stage-combine terms per batch of loads (rk4 needs <= 4, dopri5 up to 7)
       // every element initialised: a conditionally-written array ends up in LOCAL memory (ncu: more local than global
       // load requests in this kernel before the change), zero-initialised it stays in 16 registers
       float4 tv[kTB];
@@ -189,11 +206,30 @@ __device__ __forceinline__ void finish_row(const RhsArgs& A, int row, int lane, 
             y.z = fmaf(ct, tv[t].z, y.z); y.w = fmaf(ct, tv[t].w, y.w);
           }
         }
+#if GRAND_EPI_TERMS_BATCH == 4
         for (int t = kTB; t < A.ep.n_terms; ++t) {
           const float ct = A.ep.coef[t];
           const float4 v = ld_stream4_hint(A.ep.term[t] + base + c, pol_stream);
           y.x = fmaf(ct, v.x, y.x); y.y = fmaf(ct, v.y, y.y); y.z = fmaf(ct, v.z, y.z); y.w = fmaf(ct, v.w, y.w);
         }
+#else
+        for (int t0 = kTB; t0 < A.ep.n_terms; t0 += kTB) {      // further batches of kTB loads, same summation order
+          float4 tw[kTB];
+#pragma unroll
+          for (int u = 0; u < kTB; ++u) {
+            tw[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (t0 + u < A.ep.n_terms) tw[u] = ld_stream4_hint(A.ep.term[t0 + u] + base + c, pol_stream);
+          }
+#pragma unroll
+          for (int u = 0; u < kTB; ++u) {
+            if (t0 + u < A.ep.n_terms) {
+              const float ct = A.ep.coef[t0 + u];
+              y.x = fmaf(ct, tw[u].x, y.x); y.y = fmaf(ct, tw[u].y, y.y);
+              y.z = fmaf(ct, tw[u].z, y.z); y.w = fmaf(ct, tw[u].w, y.w);
+            }
+          }
+        }
+#endif
         // y_out is the next stage's gather source: keep it cacheable
         *reinterpret_cast<float4*>(A.ep.y_out + base + c) = y;
       }
@@ -357,7 +393,7 @@ rhs_window_kernel(const __grid_constant__ RhsArgs A) {
           }
           float m, l, e;
           if (split < 0) {
-            m = seg_max_redux(s, smask);
+            m = GRAND_SEG_MAX(s);
             e = valid ? expf(s - m) : 0.f;
             l = seg_sum(e, lane, lo, hi);
           } else {
@@ -374,7 +410,7 @@ rhs_window_kernel(const __grid_constant__ RhsArgs A) {
         if (valid) s = fused_score(A.a, qi + h * A.a.dk, kj + h * A.a.dk, vec4) * ew;
         float m, l, e;
         if (split < 0) {
-          m = seg_max_redux(s, smask);
+          m = GRAND_SEG_MAX(s);
           e = valid ? expf(s - m) : 0.f;
           l = seg_sum(e, lane, lo, hi);
         } else {
