@@ -40,6 +40,23 @@ constexpr int kRhsWarps = kRhsThreads / kWarp;
 //                              non-uniform-mask redux expands to ~28 instructions per call)
 //   GRAND_EPI_TERMS_BATCH=2    stage-combine terms loaded two at a time (8 instead of 16 registers in the epilogue; the
 //                              40-register build spills there)
+//   GRAND_WINDOW_L2_PREFETCH=0 no L2 prefetch of the window's epilogue rows at window start (~35 instructions per window;
+//                              added when the epilogue loads were the top stall, may no longer pay)
+//   GRAND_PERSISTENT=k         k > 0: at most k x (SMs x resident blocks) blocks are launched and every warp loops over
+//                              its windows (amortises the ~100-instruction per-window prologue; register staging only)
+#ifndef GRAND_PERSISTENT
+#define GRAND_PERSISTENT 0
+#endif
+#if GRAND_PERSISTENT
+#define GRAND_EXIT_WINDOW continue
+#define GRAND_EXIT_ROWLOOP break
+#else
+#define GRAND_EXIT_WINDOW return
+#define GRAND_EXIT_ROWLOOP return
+#endif
+#ifndef GRAND_WINDOW_L2_PREFETCH
+#define GRAND_WINDOW_L2_PREFETCH 1
+#endif
 #ifndef GRAND_SEGMAX_SHUFFLE
 #define GRAND_SEGMAX_SHUFFLE 0
 #endif
@@ -287,8 +304,12 @@ rhs_window_kernel(const __grid_constant__ RhsArgs A) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
+#if GRAND_PERSISTENT
+  for (int t = A.tile_begin + blockIdx.x * kRhsWarps + warp; t < A.tile_end; t += gridDim.x * kRhsWarps) {
+#else
   const int t = A.tile_begin + blockIdx.x * kRhsWarps + warp;
   if (t >= A.tile_end) return;
+#endif
   const int d = A.d;
   const int row_bytes = d * (int)sizeof(float);
 
@@ -333,6 +354,7 @@ rhs_window_kernel(const __grid_constant__ RhsArgs A) {
     }
   }
   // epilogue inputs of the window's rows: contiguous rows, pull them towards L2 now (one 128-byte line per lane)
+#if GRAND_WINDOW_L2_PREFETCH
   if (VEC == 4) {
     const int lines = (nrows * row_bytes + 127) >> 7;
     for (int ln = lane; ln < lines; ln += kWarp) {
@@ -341,6 +363,7 @@ rhs_window_kernel(const __grid_constant__ RhsArgs A) {
       for (int tt = 0; tt < A.ep.n_terms; ++tt) prefetch_l2(reinterpret_cast<const char*>(A.ep.term[tt]) + off);
     }
   }
+#endif
 
   // ---- level 2b: per-edge weight ab = head-mean attention (or the given weight) -------------------------------------
   float ab = 0.f;
@@ -512,7 +535,7 @@ rhs_window_kernel(const __grid_constant__ RhsArgs A) {
       }
       finish_row<VEC, R>(A, row0 + r0, lane, alpha, beta, pol_stream, acc);
     }
-    return;
+    GRAND_EXIT_WINDOW;
   }
 
   for (int kr = 0; kr < nrows; ++kr) {
@@ -591,7 +614,7 @@ rhs_window_kernel(const __grid_constant__ RhsArgs A) {
     int old = 0;
     if (lane == 0) old = atomicAdd(A.split_counter + split, 1);
     old = __shfl_sync(kFull, old, 0);
-    if (old != slot1 - slot0 - 1) return;
+    if (old != slot1 - slot0 - 1) GRAND_EXIT_ROWLOOP;
     __threadfence();
 #pragma unroll
     for (int r = 0; r < R; ++r)
@@ -642,6 +665,9 @@ rhs_window_kernel(const __grid_constant__ RhsArgs A) {
     if (lane == 0) A.split_counter[split] = 0;   // leave the counter ready for the next launch
     finish_row<VEC, R>(A, row0, lane, alpha, beta, pol_stream, acc);
   }
+#if GRAND_PERSISTENT
+  }
+#endif
 }
 
 // ---- launchers ------------------------------------------------------------------------------------------------------------
@@ -663,8 +689,14 @@ static int stage_mode() {
 
 template <int MODE, int VEC, int R, int STAGE>
 static int launch_rhs_inst(const RhsArgs& A, cudaStream_t stream) {
-  const int grid = (A.tile_end - A.tile_begin + kRhsWarps - 1) / kRhsWarps;
+  int grid = (A.tile_end - A.tile_begin + kRhsWarps - 1) / kRhsWarps;
   if (grid <= 0) return GRAND_OK;
+#if GRAND_PERSISTENT
+  if (STAGE == STAGE_DIRECT || STAGE == STAGE_ROWBUF) {   // the shared-memory stagings keep one window per warp
+    const int cap = num_sms() * GRAND_DIRECT_MINBLOCKS * GRAND_PERSISTENT;
+    if (grid > cap) grid = cap;
+  }
+#endif
   size_t smem = 0;
   if (STAGE == STAGE_CPASYNC || STAGE == STAGE_BULK) smem = (size_t)kRhsWarps * ((size_t)GRAND_TILE * A.d * sizeof(float) + 16);
   if (STAGE == STAGE_ROWBUF) smem = (size_t)kRhsWarps * GRAND_MAX_PACKED_ROWS * A.d * sizeof(float);
