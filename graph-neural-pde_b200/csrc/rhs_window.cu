@@ -44,6 +44,12 @@ constexpr int kRhsWarps = kRhsThreads / kWarp;
 //                              added when the epilogue loads were the top stall, may no longer pay)
 //   GRAND_PERSISTENT=k         k > 0: at most k x (SMs x resident blocks) blocks are launched and every warp loops over
 //                              its windows (amortises the ~100-instruction per-window prologue; register staging only)
+//   GRAND_GATHER_FIRST=1       the first batch of the window's first row is requested BEFORE the score phase, so its
+//                              latency overlaps the Q / K round trip and the softmax (needs registers: pair it with
+//                              GRAND_DIRECT_MINBLOCKS=8 or 10)
+#ifndef GRAND_GATHER_FIRST
+#define GRAND_GATHER_FIRST 0
+#endif
 #ifndef GRAND_PERSISTENT
 #define GRAND_PERSISTENT 0
 #endif
@@ -365,6 +371,28 @@ rhs_window_kernel(const __grid_constant__ RhsArgs A) {
   }
 #endif
 
+#if GRAND_GATHER_FIRST
+  // neighbour rows of the first batch of the window's first row: in flight across the whole score phase
+  constexpr int kPre = (kDirectBatch / R) < 2 ? 2 : (kDirectBatch / R);
+  float4 pre[kPre][R];
+  int pre_n = 0, pre_lo = 0;
+  if (STAGE == STAGE_DIRECT && VEC == 4) {
+    const int rr0 = __shfl_sync(kFull, rec.y, 0);
+    pre_lo = split < 0 ? ((rr0 >> 20) & 0x3f) : 0;
+    const int pre_hi = split < 0 ? ((rr0 >> 26) & 0x3f) : cnt;
+    pre_n = pre_hi - pre_lo < kPre ? pre_hi - pre_lo : kPre;
+#pragma unroll
+    for (int u = 0; u < kPre; ++u) {
+      const int ju = __shfl_sync(kFull, j, (pre_lo + u) & 31);
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        pre[u][r] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (u < pre_n && (lane + r * kWarp) * 4 < d)
+          pre[u][r] = ldg4_hint(A.x + (size_t)ju * d + (lane + r * kWarp) * 4, pol_keep);
+      }
+    }
+  }
+#endif
   // ---- level 2b: per-edge weight ab = head-mean attention (or the given weight) -------------------------------------
   float ab = 0.f;
   if (MODE == MODE_WEIGHT) {
@@ -585,6 +613,22 @@ rhs_window_kernel(const __grid_constant__ RhsArgs A) {
       constexpr int U = (kDirectBatch / R) < 2 ? 2 : (kDirectBatch / R);
       const float* xl = A.x + (size_t)lane * VEC;
       int e = e_lo;
+#if GRAND_GATHER_FIRST
+      if (VEC == 4 && kr == 0 && pre_n > 0) {        // the rows requested before the score phase (pre_lo == e_lo)
+#pragma unroll
+        for (int u = 0; u < kPre; ++u) {
+          const float a = __shfl_sync(kFull, ab, (pre_lo + u) & 31);
+          if (u < pre_n) {
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+              acc[r][0] = fmaf(a, pre[u][r].x, acc[r][0]); acc[r][1 % VEC] = fmaf(a, pre[u][r].y, acc[r][1 % VEC]);
+              acc[r][2 % VEC] = fmaf(a, pre[u][r].z, acc[r][2 % VEC]); acc[r][3 % VEC] = fmaf(a, pre[u][r].w, acc[r][3 % VEC]);
+            }
+          }
+        }
+        e += pre_n;
+      }
+#endif
       while (e_hi - e >= U) { gather_batch<VEC, R, U>(xl, d, lane, full, j, ab, e, pol_keep, acc); e += U; }
       if (U >= 8 && e_hi - e >= 4) { gather_batch<VEC, R, 4>(xl, d, lane, full, j, ab, e, pol_keep, acc); e += 4; }
       if (U >= 4 && e_hi - e >= 2) { gather_batch<VEC, R, 2>(xl, d, lane, full, j, ab, e, pol_keep, acc); e += 2; }
