@@ -12,9 +12,10 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get('GRAND_LIB') or os.path.join(HERE, 'libgrand_b200.so')   # GRAND_LIB: A/B builds
 
 GRAND_TILE = 32
+GRAND_SEG_EDGES = int(os.environ.get('GRAND_SEG_EDGES', '256'))   # rows longer than this are cut into segments
 GRAND_MAX_HEADS = 8
 GRAND_MAX_TERMS = 8
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 SCORE_TYPES = {'scaled_dot': 0, 'cosine_sim': 1, 'pearson': 2, 'exp_kernel': 3, 'exp_kernel2': 4, 'gat': 5}
 NORM_SOFTMAX, NORM_SQUAREPLUS = 0, 1
@@ -29,7 +30,9 @@ class GrandGraph(C.Structure):
               ('n_split_rows', C.c_int32), ('n_split_tiles', C.c_int32),
               ('rowptr', C.c_void_p), ('col', C.c_void_p), ('erow', C.c_void_p), ('eid', C.c_void_p),
               ('win_hdr', C.c_void_p), ('win_rec', C.c_void_p),
-              ('split_tile0', C.c_void_p), ('colptr', C.c_void_p), ('csc_pos', C.c_void_p)]
+              ('split_tile0', C.c_void_p), ('colptr', C.c_void_p), ('csc_pos', C.c_void_p),
+              ('n_lunits', C.c_int32), ('n_munits', C.c_int32), ('n_lrows', C.c_int32),
+              ('seg_desc', C.c_void_p), ('lrow_slot0', C.c_void_p), ('lrow_row', C.c_void_p)]
 
 
 class GrandAttention(C.Structure):
@@ -49,7 +52,7 @@ class GrandEpilogue(C.Structure):
 class GrandWorkspace(C.Structure):
   _fields_ = [('q', C.c_void_p), ('k', C.c_void_p), ('scores', C.c_void_p), ('seg_stats', C.c_void_p),
               ('split_stats', C.c_void_p), ('row_stats', C.c_void_p), ('split_partial', C.c_void_p), ('split_counter', C.c_void_p),
-              ('gmax', C.c_void_p)]
+              ('gmax', C.c_void_p), ('lrow_stats', C.c_void_p), ('lpartial', C.c_void_p), ('lcounter', C.c_void_p)]
 
 
 # every symbol include/grand_b200.h declares: name -> (restype, argtypes)
@@ -58,7 +61,7 @@ SIGNATURES = {
   'grand_abi_version': (C.c_int, []),
   'grand_last_error': (C.c_char_p, []),
   'grand_launch_count': (C.c_int64, []),
-  'grand_workspace_sizes': (C.c_int, [C.POINTER(GrandGraph), C.POINTER(GrandAttention)] + [C.POINTER(C.c_int64)] * 7),
+  'grand_workspace_sizes': (C.c_int, [C.POINTER(GrandGraph), C.POINTER(GrandAttention)] + [C.POINTER(C.c_int64)] * 10),
   'grand_project_qk': (C.c_int, [_P, C.c_int32, C.c_int32, C.POINTER(GrandAttention), _P, _P, _P]),
   'grand_rhs_attention': (C.c_int, [C.POINTER(GrandGraph), C.POINTER(GrandAttention), _P, C.POINTER(GrandWorkspace),
                                      C.POINTER(GrandEpilogue), _P]),

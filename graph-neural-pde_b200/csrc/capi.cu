@@ -125,7 +125,7 @@ const char* grand_last_error(void) { return g_error; }
 
 int grand_workspace_sizes(const grand_graph* g, const grand_attention* a, int64_t* n_q, int64_t* n_k,
                           int64_t* n_scores, int64_t* n_seg_stats, int64_t* n_split_stats, int64_t* n_split_partial,
-                          int64_t* n_split_counter) {
+                          int64_t* n_split_counter, int64_t* n_lrow_stats, int64_t* n_lpartial, int64_t* n_lcounter) {
   GRAND_REQUIRE(g != nullptr, GRAND_EINVAL, "workspace_sizes: graph is null");
   const int64_t ad_eff = a ? (a->score_type == GRAND_SCORE_EXP_KERNEL2 ? 2 * a->ad : a->ad) : 0;
   const int64_t heads = a ? a->heads : 0;
@@ -137,6 +137,9 @@ int grand_workspace_sizes(const grand_graph* g, const grand_attention* a, int64_
   if (n_split_stats) *n_split_stats = (int64_t)g->n_split_tiles * heads * 2;
   if (n_split_partial) *n_split_partial = (int64_t)g->n_split_tiles * d;
   if (n_split_counter) *n_split_counter = g->n_split_rows;
+  if (n_lrow_stats) *n_lrow_stats = (int64_t)g->n_lunits * heads * 2;
+  if (n_lpartial) *n_lpartial = (int64_t)g->n_lunits * d;
+  if (n_lcounter) *n_lcounter = g->n_lrows;
   return GRAND_OK;
 }
 

@@ -24,6 +24,12 @@ struct GraphView {
   const int *rowptr, *col, *erow, *eid, *split_tile0, *colptr, *csc_pos;
   const int4* win_hdr;
   const int2* win_rec;
+  // row segments of the persistent edge kernel (rhs_stream.cu): rows with more than GRAND_TILE in-edges are handled
+  // whole by one warp (<= seg_edges edges: "medium") or cut into segments of seg_edges edges ("long")
+  int n_lunits, n_munits, n_lrows;
+  const int4* seg_desc;      // [n_lunits + n_munits]: row, first CSR position, edge count, long-row index or -1
+  const int* lrow_slot0;     // [n_lrows + 1] first segment (== partial-sum slot) of each long row
+  const int* lrow_row;       // [n_lrows] row id of each long row
 };
 
 struct EpiView {
@@ -55,6 +61,9 @@ struct RhsArgs {
   float* row_stats;          // [n_split_rows, H, 2] merged per long row
   float* split_partial;      // [n_split_tiles, d]
   int* split_counter;        // [n_split_rows]
+  float* lrow_stats;         // [n_lunits, H, 2] softmax (max, sum-exp) of every long-row segment (rhs_stream.cu pre-pass)
+  float* lpartial;           // [n_lunits, d] partial sums of the long-row segments
+  int* lcounter;             // [n_lrows] arrival counters (atomicInc wraps them back to zero)
   int l2_hints;              // bit 0: evict_last on the gathers, bit 1: evict_first on the streams
   int tile_begin, tile_end;  // window range of this launch (chunk tiles and packed windows may go to different streams)
 };

@@ -126,6 +126,9 @@ static GraphView view(const grand_graph* g) {
   v.split_tile0 = g->split_tile0; v.colptr = g->colptr; v.csc_pos = g->csc_pos;
   v.win_hdr = reinterpret_cast<const int4*>(g->win_hdr);
   v.win_rec = reinterpret_cast<const int2*>(g->win_rec);
+  v.n_lunits = g->n_lunits; v.n_munits = g->n_munits; v.n_lrows = g->n_lrows;
+  v.seg_desc = reinterpret_cast<const int4*>(g->seg_desc);
+  v.lrow_slot0 = g->lrow_slot0; v.lrow_row = g->lrow_row;
   return v;
 }
 
@@ -195,6 +198,8 @@ static int check_graph(const grand_graph* g) {
 }
 
 int launch_rhs_mode(int mode, const RhsArgs& A, cudaStream_t stream);
+int launch_stream_mode(int mode, const RhsArgs& A, cudaStream_t stream);
+bool stream_kernel_ok(const RhsArgs& A);
 
 // One non-blocking side stream + fork/join events per device, created on first use and kept for the life of the
 // process (the only state this library owns; GRAND_FORK=1 enables the fork).
@@ -288,15 +293,22 @@ int rhs_attention_impl(const grand_graph* g, const grand_attention* a, const flo
   A.l2_hints = l2_hints();
   A.split_stats = ws->split_stats; A.row_stats = ws->row_stats; A.split_partial = ws->split_partial;
   A.split_counter = ws->split_counter;
-  GRAND_REQUIRE(g->n_split_tiles == 0 || (ws->split_partial && ws->split_counter), GRAND_EINVAL,
+  A.lrow_stats = ws->lrow_stats; A.lpartial = ws->lpartial; A.lcounter = ws->lcounter;
+  A.tile_begin = 0;
+  A.tile_end = g->n_tiles;
+  const bool stream_ok = stream_kernel_ok(A);
+  GRAND_REQUIRE(stream_ok || g->n_split_tiles == 0 || (ws->split_partial && ws->split_counter), GRAND_EINVAL,
                 "graph has split rows: workspace split_partial / split_counter are null");
   if (project) {
     rc = launch_project_qk(x, g->n_rows, g->n_cols, a->d, a->wq, a->bq, a->wk, a->bk, A.a.ad_eff, ws->q, ws->k,
                            stream);
     if (rc != GRAND_OK) return rc;
   }
-  A.tile_begin = 0;
-  A.tile_end = g->n_tiles;
+  if (stream_ok) {
+    if (fused_ok(A.a)) return launch_stream_mode(MODE_FUSED, A, stream);
+    if ((rc = run_general_prepass(A.g, A.a, ws, stream)) != GRAND_OK) return rc;
+    return launch_stream_mode(MODE_PRECOMP, A, stream);
+  }
   if (fused_ok(A.a)) {
     if (g->n_split_tiles == 0) return launch_rhs_mode(MODE_FUSED, A, stream);
     GRAND_REQUIRE(ws->split_stats != nullptr && ws->row_stats != nullptr, GRAND_EINVAL,
@@ -344,6 +356,7 @@ int rhs_attention_backward_host(const grand_graph* g, const grand_attention* a, 
   A.x = x; A.q = ws->q; A.k = ws->k;
   A.split_stats = ws->split_stats; A.row_stats = ws->row_stats; A.split_partial = ws->split_partial;
   A.split_counter = ws->split_counter;
+  A.lrow_stats = nullptr; A.lpartial = nullptr; A.lcounter = nullptr;
   rc = launch_project_qk(x, g->n_rows, g->n_cols, a->d, a->wq, a->bq, a->wk, a->bk, A.a.ad_eff, ws->q, ws->k, stream);
   if (rc != GRAND_OK) return rc;
   if (g->n_split_tiles > 0) {
@@ -362,8 +375,6 @@ int rhs_laplacian_impl(const grand_graph* g, int d, const float* x, const float*
   if ((rc = check_epilogue(ep)) != GRAND_OK) return rc;
   GRAND_REQUIRE(x != nullptr && (w_csr != nullptr || g->n_edges == 0), GRAND_EINVAL, "rhs_laplacian: null argument");
   GRAND_REQUIRE(d > 0, GRAND_EINVAL, "rhs_laplacian: d = %d", d);
-  GRAND_REQUIRE(g->n_split_tiles == 0 || (ws && ws->split_partial && ws->split_counter), GRAND_EINVAL,
-                "graph has split rows: workspace split_partial / split_counter are null");
   RhsArgs A;
   A.g = view(g);
   A.a = AttnView{};
@@ -376,6 +387,12 @@ int rhs_laplacian_impl(const grand_graph* g, int d, const float* x, const float*
   A.tile_end = g->n_tiles;
   A.split_partial = ws ? ws->split_partial : nullptr;
   A.split_counter = ws ? ws->split_counter : nullptr;
+  A.lrow_stats = nullptr;
+  A.lpartial = ws ? ws->lpartial : nullptr;
+  A.lcounter = ws ? ws->lcounter : nullptr;
+  if (stream_kernel_ok(A)) return launch_stream_mode(MODE_WEIGHT, A, stream);
+  GRAND_REQUIRE(g->n_split_tiles == 0 || (ws && ws->split_partial && ws->split_counter), GRAND_EINVAL,
+                "graph has split rows: workspace split_partial / split_counter are null");
   return launch_rhs_mode(MODE_WEIGHT, A, stream);
 }
 

@@ -102,7 +102,9 @@ class RhsEngine:
                 seg_stats=f(p.n_cols * heads * 2), split_stats=f(p.n_split_tiles * max(heads, 1) * 2),
                 row_stats=f(p.n_split_rows * max(heads, 1) * 2),
                 split_partial=f(p.n_split_tiles * self.d),
-                split_counter=torch.zeros(max(p.n_split_rows, 1), dtype=torch.int32, device=dev), gmax=f(1))
+                split_counter=torch.zeros(max(p.n_split_rows, 1), dtype=torch.int32, device=dev), gmax=f(1),
+                lrow_stats=f(p.n_lunits * max(heads, 1) * 2), lpartial=f(p.n_lunits * self.d),
+                lcounter=torch.zeros(max(p.n_lrows, 1), dtype=torch.int32, device=dev))
     ws = N.GrandWorkspace()
     for name, t in keep.items():
       setattr(ws, name, t.data_ptr())

@@ -35,7 +35,8 @@ def pack_short_rows(deg, tile, max_rows):
 
 
 class GraphPlan:
-  def __init__(self, edge_index, num_nodes, device=None, num_cols=None, tile=N.GRAND_TILE, max_rows=8):
+  def __init__(self, edge_index, num_nodes, device=None, num_cols=None, tile=N.GRAND_TILE, max_rows=8,
+               seg_edges=N.GRAND_SEG_EDGES):
     assert edge_index.dim() == 2 and edge_index.shape[0] == 2, 'edge_index must be [2, E]'
     device = torch.device(device) if device is not None else edge_index.device
     ei = edge_index.to(device=device, dtype=torch.long)
@@ -110,6 +111,27 @@ class GraphPlan:
     colptr = torch.zeros(n_cols + 1, dtype=torch.long, device=device)
     colptr[1:] = torch.cumsum(cdeg, 0)
 
+    # ---- work list of the persistent edge kernel (csrc/rhs_stream.cu): rows with more than `tile` in-edges are either
+    #      "medium" (<= seg_edges: one warp takes the whole row) or "long" (cut into segments of seg_edges edges whose
+    #      partial sums are merged by the last segment to finish).  Longest first: the tail of the kernel is made of the
+    #      small packed windows.
+    assert seg_edges >= tile and seg_edges % tile == 0
+    long_rows = torch.nonzero(deg > seg_edges).flatten()
+    long_rows = long_rows[torch.argsort(deg[long_rows], descending=True, stable=True)]
+    med_rows = torch.nonzero((deg > tile) & (deg <= seg_edges)).flatten()
+    med_rows = med_rows[torch.argsort(deg[med_rows], descending=True, stable=True)]
+    nseg = (deg[long_rows] + seg_edges - 1) // seg_edges
+    lrow_slot0 = torch.zeros(long_rows.numel() + 1, dtype=torch.long, device=device)
+    lrow_slot0[1:] = torch.cumsum(nseg, 0)
+    n_lunits = int(lrow_slot0[-1])
+    l_index = torch.repeat_interleave(torch.arange(long_rows.numel(), device=device), nseg)
+    l_k = torch.arange(n_lunits, device=device) - lrow_slot0[:-1][l_index]
+    l_row = long_rows[l_index]
+    l_beg = rowptr[l_row] + l_k * seg_edges
+    l_cnt = torch.minimum(torch.full_like(l_beg, seg_edges), rowptr[l_row + 1] - l_beg)
+    seg_desc = torch.cat([torch.stack([l_row, l_beg, l_cnt, l_index], dim=1),
+                          torch.stack([med_rows, rowptr[med_rows], deg[med_rows], torch.full_like(med_rows, -1)], dim=1)])
+
     i32 = lambda t: t.to(torch.int32).contiguous()
     self.device = device
     self.n_rows, self.n_cols, self.n_edges = n_rows, n_cols, e
@@ -123,6 +145,9 @@ class GraphPlan:
     self.win_hdr, self.win_rec = i32(win_hdr), i32(win_rec)
     self.split_tile0 = i32(split_tile0)
     self.colptr, self.csc_pos = i32(colptr), i32(perm_c)
+    self.seg_edges = int(seg_edges)
+    self.n_lunits, self.n_munits, self.n_lrows = n_lunits, int(med_rows.numel()), int(long_rows.numel())
+    self.seg_desc, self.lrow_slot0, self.lrow_row = i32(seg_desc), i32(lrow_slot0), i32(long_rows)
     self.eid_long = perm  # CSR position -> caller position (int64, for torch-side permutations)
     self._struct = None
 
@@ -132,7 +157,9 @@ class GraphPlan:
       g = N.GrandGraph()
       g.n_rows, g.n_cols, g.n_edges, g.n_tiles = self.n_rows, self.n_cols, self.n_edges, self.n_tiles
       g.n_split_rows, g.n_split_tiles = self.n_split_rows, self.n_split_tiles
-      for name in ('rowptr', 'col', 'erow', 'eid', 'win_hdr', 'win_rec', 'split_tile0', 'colptr', 'csc_pos'):
+      g.n_lunits, g.n_munits, g.n_lrows = self.n_lunits, self.n_munits, self.n_lrows
+      for name in ('rowptr', 'col', 'erow', 'eid', 'win_hdr', 'win_rec', 'split_tile0', 'colptr', 'csc_pos',
+                   'seg_desc', 'lrow_slot0', 'lrow_row'):
         setattr(g, name, getattr(self, name).data_ptr())
       self._struct = g
     return self._struct

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define GRAND_ABI_VERSION 1
+#define GRAND_ABI_VERSION 2
 
 /* error codes */
 #define GRAND_OK 0
@@ -82,6 +82,16 @@ typedef struct grand_graph {
   const int32_t* split_tile0;  /* [n_split_rows + 1] first split-tile slot of each split row          */
   const int32_t* colptr;       /* [n_cols + 1] CSC by edge_index[1] (may be null if norm_idx 1 unused)*/
   const int32_t* csc_pos;      /* [n_edges] CSC position -> CSR position                              */
+  /* Work list of the persistent edge kernel (csrc/rhs_stream.cu).  Rows with <= GRAND_TILE in-edges are the packed
+   * windows [n_split_tiles, n_tiles) above; a row with more is ONE "medium" unit (<= seg_edges in-edges, a warp takes
+   * the whole row) or is cut into "long" segments of seg_edges edges.  Units are ordered long segments (longest row
+   * first), medium rows (longest first), packed windows (row order).  seg_desc may be null when n_split_tiles == 0. */
+  int32_t n_lunits;            /* long-row segments; unit index == partial-sum slot                   */
+  int32_t n_munits;            /* medium rows                                                         */
+  int32_t n_lrows;             /* rows cut into long segments                                         */
+  const int32_t* seg_desc;     /* [n_lunits + n_munits, 4]: row, first CSR position, edge count, long-row index or -1 */
+  const int32_t* lrow_slot0;   /* [n_lrows + 1] first segment of each long row                        */
+  const int32_t* lrow_row;     /* [n_lrows] row id of each long row                                   */
 } grand_graph;
 
 /*
@@ -135,6 +145,9 @@ typedef struct grand_workspace {
   float* split_partial;        /* [n_split_tiles, d]                                                  */
   int32_t* split_counter;      /* [n_split_rows], zero on first use; kernels leave it zero            */
   float* gmax;                 /* [1] global max for squareplus (ordered-int encoded during reduction)*/
+  float* lrow_stats;           /* [n_lunits, heads, 2] softmax (max, sum-exp) of every long-row segment */
+  float* lpartial;             /* [n_lunits, d] partial sums of the long-row segments                 */
+  int32_t* lcounter;           /* [n_lrows], zero on first use; the kernel leaves it zero (atomicInc wraps) */
 } grand_workspace;
 
 int grand_abi_version(void);
@@ -145,7 +158,8 @@ const char* grand_last_error(void);
 /* element counts of each workspace array for a graph / attention shape; any pointer may be null */
 int grand_workspace_sizes(const grand_graph* g, const grand_attention* a, int64_t* n_q, int64_t* n_k,
                           int64_t* n_scores, int64_t* n_seg_stats, int64_t* n_split_stats,
-                          int64_t* n_split_partial, int64_t* n_split_counter);
+                          int64_t* n_split_partial, int64_t* n_split_counter, int64_t* n_lrow_stats,
+                          int64_t* n_lpartial, int64_t* n_lcounter);
 
 /* Q = x Wq^T + bq over n_rows rows, K = x Wk^T + bk over n_cols rows.
  * Replaces the Q/K nn.Linear calls, reference src/function_transformer_attention.py:174-175 (V, :176, is unused on

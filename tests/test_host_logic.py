@@ -92,6 +92,44 @@ def test_graph_plan_invariants():
   assert torch.equal(p.colptr.long()[1:] - p.colptr.long()[:-1], cdeg)
 
 
+def test_stream_work_list_covers_every_edge_once():
+  """Units of the persistent edge kernel (csrc/rhs_stream.cu): long segments, medium rows, packed windows."""
+  n = 400
+  ei = make_graph(n, 3000, max_degree=350, seed=2)
+  ei = torch.cat([ei, torch.stack([torch.arange(n), torch.arange(n)])], dim=1)
+  for seg in (32, 64, 256):
+    p = GraphPlan(ei, n, device='cpu', seg_edges=seg)
+    deg = (p.rowptr[1:] - p.rowptr[:-1]).long()
+    covered = torch.zeros(p.n_edges, dtype=torch.int32)
+    rows_done = torch.zeros(n, dtype=torch.int32)
+    sd = p.seg_desc.long()
+    assert sd.shape == (p.n_lunits + p.n_munits, 4)
+    for u in range(sd.shape[0]):
+      row, beg, cnt, split = (int(v) for v in sd[u])
+      assert N.GRAND_TILE < int(deg[row]) and 0 < cnt <= seg
+      assert int(p.rowptr[row]) <= beg and beg + cnt <= int(p.rowptr[row + 1])
+      covered[beg:beg + cnt] += 1
+      if u < p.n_lunits:
+        assert int(deg[row]) > seg and int(p.lrow_row[split]) == row
+        assert int(p.lrow_slot0[split]) <= u < int(p.lrow_slot0[split + 1])
+        assert beg == int(p.rowptr[row]) + (u - int(p.lrow_slot0[split])) * seg
+      else:
+        assert split == -1 and cnt == int(deg[row]) <= seg and beg == int(p.rowptr[row])
+        rows_done[row] += 1
+    rows_done[p.lrow_row.long()] += 1
+    if p.n_lunits + p.n_munits > 1:   # longest first inside each class
+      c = sd[:, 2]
+      first = sd[p.lrow_slot0[:-1].long(), 0] if p.n_lrows else sd[:0, 0]
+      assert bool((deg[first][1:] <= deg[first][:-1]).all())
+      assert bool((c[p.n_lunits:][1:] <= c[p.n_lunits:][:-1]).all())
+    for t in range(p.n_split_tiles, p.n_tiles):
+      r, b, nr = int(p.tile_row[t]), int(p.tile_beg[t]), int(p.tile_nrows[t])
+      covered[b:int(p.rowptr[r + nr])] += 1
+      rows_done[r:r + nr] += 1
+    assert bool((covered == 1).all()) and bool((rows_done == 1).all())
+    assert p.n_lrows == int((deg > seg).sum()) and p.n_munits == int(((deg > N.GRAND_TILE) & (deg <= seg)).sum())
+
+
 def test_plan_with_isolated_nodes_and_no_edges():
   p = GraphPlan(torch.zeros((2, 0), dtype=torch.long), 5, device='cpu')
   assert int(p.tile_nrows.sum()) == 5 and p.n_edges == 0 and p.n_split_tiles == 0
