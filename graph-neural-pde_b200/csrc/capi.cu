@@ -138,7 +138,7 @@ int grand_workspace_sizes(const grand_graph* g, const grand_attention* a, int64_
   if (n_split_partial) *n_split_partial = (int64_t)g->n_split_tiles * d;
   if (n_split_counter) *n_split_counter = g->n_split_rows;
   if (n_lrow_stats) *n_lrow_stats = (int64_t)g->n_lunits * heads * 2;
-  if (n_lpartial) *n_lpartial = (int64_t)g->n_lunits * d;
+  if (n_lpartial) *n_lpartial = (int64_t)g->n_lunits * (heads > 0 ? heads : 1) * d;
   if (n_lcounter) *n_lcounter = g->n_lrows;
   return GRAND_OK;
 }

@@ -62,7 +62,7 @@ struct RhsArgs {
   float* split_partial;      // [n_split_tiles, d]
   int* split_counter;        // [n_split_rows]
   float* lrow_stats;         // [n_lunits, H, 2] softmax (max, sum-exp) of every long-row segment (rhs_stream.cu pre-pass)
-  float* lpartial;           // [n_lunits, d] partial sums of the long-row segments
+  float* lpartial;           // [n_lunits, max(H,1), d] partial sums of the long-row segments (per head in MODE_FUSED)
   int* lcounter;             // [n_lrows] arrival counters (atomicInc wraps them back to zero)
   int l2_hints;              // bit 0: evict_last on the gathers, bit 1: evict_first on the streams
   int tile_begin, tile_end;  // window range of this launch (chunk tiles and packed windows may go to different streams)
@@ -142,6 +142,22 @@ __device__ __forceinline__ void st_stream4_hint(float* p, float4 v, uint64_t pol
   asm volatile("st.global.L1::no_allocate.L2::cache_hint.v4.f32 [%0], {%1,%2,%3,%4}, %5;" ::"l"(p), "f"(v.x),
                "f"(v.y), "f"(v.z), "f"(v.w), "l"(policy)
                : "memory");
+}
+// 256-bit read-only load (sm_100a: SASS LDG.E.256): a 64-byte K / Q row is two of these instead of four 128-bit loads --
+// half the instructions and, for a lane-per-edge gather that touches 32 different lines, half the L1 wavefronts
+struct float8 {
+  float4 lo, hi;
+};
+__device__ __forceinline__ float8 ldg8(const float* p) {
+  float8 r;
+  asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=f"(r.lo.x), "=f"(r.lo.y), "=f"(r.lo.z), "=f"(r.lo.w), "=f"(r.hi.x), "=f"(r.hi.y), "=f"(r.hi.z),
+                 "=f"(r.hi.w)
+               : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void prefetch_l2_keep(const void* p) {
+  asm volatile("prefetch.global.L2::evict_last [%0];" ::"l"(p));
 }
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }

@@ -222,6 +222,23 @@ static SideStream* side_stream() {
   }
   return &table[dev];
 }
+// fork / join of the library's side stream around a pair of independent launches (captured into CUDA Graphs as two
+// parallel branches)
+int side_fork(cudaStream_t stream, cudaStream_t* side) {
+  SideStream* ss = side_stream();
+  GRAND_REQUIRE(ss != nullptr, GRAND_ECUDA, "could not create the side stream");
+  GRAND_CUDA_OK(cudaEventRecord(ss->fork, stream));
+  GRAND_CUDA_OK(cudaStreamWaitEvent(ss->stream, ss->fork, 0));
+  *side = ss->stream;
+  return GRAND_OK;
+}
+int side_join(cudaStream_t stream) {
+  SideStream* ss = side_stream();
+  GRAND_REQUIRE(ss != nullptr, GRAND_ECUDA, "could not create the side stream");
+  GRAND_CUDA_OK(cudaEventRecord(ss->join, ss->stream));
+  GRAND_CUDA_OK(cudaStreamWaitEvent(stream, ss->join, 0));
+  return GRAND_OK;
+}
 static bool fork_enabled() {
   static int v = -1;
   if (v < 0) {

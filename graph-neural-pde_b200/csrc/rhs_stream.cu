@@ -27,7 +27,7 @@
 namespace grand {
 
 #ifndef GRAND_STREAM_THREADS
-#define GRAND_STREAM_THREADS 384
+#define GRAND_STREAM_THREADS 320
 #endif
 #ifndef GRAND_STREAM_MINBLOCKS
 #define GRAND_STREAM_MINBLOCKS 2

@@ -103,7 +103,7 @@ class RhsEngine:
                 row_stats=f(p.n_split_rows * max(heads, 1) * 2),
                 split_partial=f(p.n_split_tiles * self.d),
                 split_counter=torch.zeros(max(p.n_split_rows, 1), dtype=torch.int32, device=dev), gmax=f(1),
-                lrow_stats=f(p.n_lunits * max(heads, 1) * 2), lpartial=f(p.n_lunits * self.d),
+                lrow_stats=f(p.n_lunits * max(heads, 1) * 2), lpartial=f(p.n_lunits * max(heads, 1) * self.d),
                 lcounter=torch.zeros(max(p.n_lrows, 1), dtype=torch.int32, device=dev))
     ws = N.GrandWorkspace()
     for name, t in keep.items():

@@ -146,7 +146,7 @@ typedef struct grand_workspace {
   int32_t* split_counter;      /* [n_split_rows], zero on first use; kernels leave it zero            */
   float* gmax;                 /* [1] global max for squareplus (ordered-int encoded during reduction)*/
   float* lrow_stats;           /* [n_lunits, heads, 2] softmax (max, sum-exp) of every long-row segment */
-  float* lpartial;             /* [n_lunits, d] partial sums of the long-row segments                 */
+  float* lpartial;             /* [n_lunits, max(heads,1), d] partial sums of the long-row segments   */
   int32_t* lcounter;           /* [n_lrows], zero on first use; the kernel leaves it zero (atomicInc wraps) */
 } grand_workspace;
 

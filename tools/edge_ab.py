@@ -75,10 +75,14 @@ def timed_graph(body, launches, repeats=5):
 def main():
   ap = argparse.ArgumentParser()
   ap.add_argument('--workload', default='ogbn-arxiv')
+  ap.add_argument('--max-degree', type=int, default=0, help='regenerate the graph with this maximum degree (hub test)')
   ap.add_argument('variants', nargs='+')
   args = ap.parse_args()
   ds, opt, x_host = bench.build_workload(args.workload, DEV)
   n, d = x_host.shape
+  if args.max_degree:
+    from graph_neural_pde_b200.synthetic import make_graph
+    ds.data.edge_index = make_graph(n, ds.data.edge_index.shape[1] // 2, max_degree=args.max_degree, seed=0)
   data = Data(x=x_host, edge_index=ds.data.edge_index, edge_attr=None, num_nodes=n)
   g = torch.Generator().manual_seed(0)
   problems = {}
