@@ -42,11 +42,21 @@ class GrandAttention(C.Structure):
               ('kernel_scalars', C.c_void_p), ('edge_weight_csr', C.c_void_p)]
 
 
+GRAND_MAX_PEERS = 8
+
+
+class GrandPeers(C.Structure):
+  _fields_ = [('world', C.c_int32), ('rank', C.c_int32), ('arena', C.c_void_p * GRAND_MAX_PEERS),
+              ('flags_offset', C.c_int64), ('push_ptr', C.c_void_p), ('push_dst', C.c_void_p),
+              ('push_src', C.c_void_p), ('n_push', C.c_int32)]
+
+
 class GrandEpilogue(C.Structure):
   _fields_ = [('alpha_train', C.c_void_p), ('beta_train', C.c_void_p), ('x0', C.c_void_p),
               ('no_alpha_sigmoid', C.c_int32), ('n_terms', C.c_int32),
               ('f_out', C.c_void_p), ('y_out', C.c_void_p), ('coef_f', C.c_float),
-              ('coef', C.c_float * GRAND_MAX_TERMS), ('term', C.c_void_p * GRAND_MAX_TERMS)]
+              ('coef', C.c_float * GRAND_MAX_TERMS), ('term', C.c_void_p * GRAND_MAX_TERMS),
+              ('peers', C.POINTER(GrandPeers))]
 
 
 class GrandWorkspace(C.Structure):
@@ -81,6 +91,18 @@ SIGNATURES = {
   'grand_lincomb': (C.c_int, [C.c_int64, C.c_int32, C.POINTER(C.c_void_p), c_float_p, _P, _P]),
   'grand_error_sumsq': (C.c_int, [C.c_int64, C.c_int32, C.POINTER(C.c_void_p), c_float_p, _P, _P, C.c_float,
                                    C.c_float, _P, _P]),
+  'grand_peer_alloc': (C.c_int, [C.c_int64, C.POINTER(C.c_void_p)]),
+  'grand_peer_free': (C.c_int, [_P]),
+  'grand_peer_export': (C.c_int, [_P, _P]),
+  'grand_peer_open': (C.c_int, [_P, C.POINTER(C.c_void_p)]),
+  'grand_peer_close': (C.c_int, [_P]),
+  'grand_peer_push_rows': (C.c_int, [C.POINTER(GrandPeers), _P, C.c_int32, C.c_int32, _P]),
+  'grand_peer_barrier': (C.c_int, [C.POINTER(GrandPeers), _P]),
+  'grand_peer_error': (C.c_int, [C.POINTER(GrandPeers), C.POINTER(C.c_int32)]),
+  'grand_integrate_fixed_sharded': (C.c_int, [C.POINTER(GrandGraph), C.POINTER(GrandAttention), C.POINTER(GrandWorkspace),
+                                               C.POINTER(GrandEpilogue), C.c_int32, c_float_p, C.c_int32, _P, _P, _P, _P,
+                                               _P, _P, C.POINTER(C.c_void_p), C.POINTER(C.c_int32),
+                                               C.POINTER(GrandPeers), _P]),
   'grand_plan_pack_rows': (C.c_int64, [_P, C.c_int64, C.c_int32, C.c_int32, _P, _P]),
 }
 

@@ -105,6 +105,59 @@ pack_rows_kernel(const float* __restrict__ x, const int* __restrict__ idx, int64
   }
 }
 
+// ---- node-partitioned multi-GPU: rows into the peers' halos, and the cross-GPU barrier -----------------------------------
+struct PeerPtrs {
+  float* out[GRAND_MAX_PEERS];
+};
+
+__global__ void __launch_bounds__(256)
+peer_push_rows_kernel(const float* __restrict__ src, int n_push, int width, const int* __restrict__ push_src,
+                      const int2* __restrict__ push_dst, PeerPtrs peers) {
+  // one thread per (push entry, 16-byte piece): no dependent chain beyond entry -> source piece -> store
+  const int pieces = width >> 2;
+  const long long n_items = (long long)n_push * pieces;
+  for (long long it = (long long)blockIdx.x * blockDim.x + threadIdx.x; it < n_items; it += (long long)gridDim.x * blockDim.x) {
+    const int entry = (int)(it / pieces), c = (int)(it - (long long)entry * pieces) * 4;
+    const int row = __ldg(push_src + entry);
+    const int2 dst = __ldg(push_dst + entry);
+    const float4 v = ldg4(src + (size_t)row * width + c);
+    *reinterpret_cast<float4*>(peers.out[dst.x] + (size_t)dst.y * width + c) = v;
+  }
+  __threadfence_system();
+}
+
+struct BarrierArgs {
+  int world, rank;
+  int* flags[GRAND_MAX_PEERS];     // flags[p]: rank p's arrival flags (int[GRAND_MAX_PEERS]); [rank] is the local one
+  int* epoch;
+  int* error;
+};
+
+__global__ void peer_barrier_kernel(BarrierArgs b) {
+  __shared__ int s_epoch;
+  if (threadIdx.x == 0) {
+    s_epoch = *b.epoch + 1;
+    *b.epoch = s_epoch;
+  }
+  __syncthreads();
+  const int epoch = s_epoch, p = threadIdx.x;
+  __threadfence_system();
+  if (p < b.world && p != b.rank) {
+    asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(b.flags[p] + b.rank), "r"(epoch) : "memory");
+    const long long t0 = clock64();
+    int seen;
+    do {
+      asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(seen) : "l"(b.flags[b.rank] + p) : "memory");
+      if (seen - epoch >= 0) break;
+      if (clock64() - t0 > 4000000000ll) {       // ~2 s at 2 GHz: a peer is gone; do not hang the GPU
+        atomicExch(b.error, epoch);
+        break;
+      }
+    } while (true);
+  }
+  __syncthreads();
+}
+
 static int elementwise_grid(int64_t n) {
   int64_t blocks = (n + 255) / 256;
   const int64_t cap = (int64_t)num_sms() * 8;
@@ -225,6 +278,171 @@ int grand_error_sumsq(int64_t n, int32_t n_terms, const float* const* k, const f
   error_sumsq_kernel<<<elementwise_grid(n), 256, 0, (cudaStream_t)stream>>>(n, a, y0, y1, atol, rtol, sumsq);
   count_launch();
   GRAND_CUDA_OK(cudaGetLastError());
+  return GRAND_OK;
+}
+
+// ---- peer arenas ------------------------------------------------------------------------------------------------------
+int grand_peer_alloc(int64_t bytes, void** ptr) {
+  GRAND_REQUIRE(bytes > 0 && ptr != nullptr, GRAND_EINVAL, "peer_alloc: bad argument");
+  GRAND_CUDA_OK(cudaMalloc(ptr, (size_t)bytes));
+  GRAND_CUDA_OK(cudaMemset(*ptr, 0, (size_t)bytes));
+  GRAND_CUDA_OK(cudaDeviceSynchronize());
+  return GRAND_OK;
+}
+int grand_peer_free(void* ptr) {
+  if (ptr != nullptr) GRAND_CUDA_OK(cudaFree(ptr));
+  return GRAND_OK;
+}
+int grand_peer_export(void* ptr, void* handle64) {
+  GRAND_REQUIRE(ptr != nullptr && handle64 != nullptr, GRAND_EINVAL, "peer_export: null argument");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  GRAND_CUDA_OK(cudaIpcGetMemHandle(reinterpret_cast<cudaIpcMemHandle_t*>(handle64), ptr));
+  return GRAND_OK;
+}
+int grand_peer_open(const void* handle64, void** ptr) {
+  GRAND_REQUIRE(ptr != nullptr && handle64 != nullptr, GRAND_EINVAL, "peer_open: null argument");
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, sizeof(h));
+  GRAND_CUDA_OK(cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return GRAND_OK;
+}
+int grand_peer_close(void* ptr) {
+  if (ptr != nullptr) GRAND_CUDA_OK(cudaIpcCloseMemHandle(ptr));
+  return GRAND_OK;
+}
+
+static int check_peers(const grand_peers* pr) {
+  GRAND_REQUIRE(pr != nullptr && pr->world >= 1 && pr->world <= GRAND_MAX_PEERS && pr->rank >= 0 && pr->rank < pr->world,
+                GRAND_EINVAL, "peers: null or bad world / rank");
+  for (int p = 0; p < pr->world; ++p) GRAND_REQUIRE(pr->arena[p] != nullptr, GRAND_EINVAL, "peers: arena %d is null", p);
+  return GRAND_OK;
+}
+
+int grand_peer_push_rows(const grand_peers* pr, const float* src, int32_t n_rows, int32_t width, void* stream) {
+  int rc;
+  if ((rc = check_peers(pr)) != GRAND_OK) return rc;
+  GRAND_REQUIRE(src != nullptr && n_rows >= 0 && width > 0 && (width & 3) == 0 && pr->push_ptr && pr->push_dst &&
+                    pr->n_push >= 0 && (pr->n_push == 0 || pr->push_src), GRAND_EINVAL, "peer_push_rows: bad argument");
+  if (n_rows == 0 || pr->world == 1 || pr->n_push == 0) return GRAND_OK;
+  const ptrdiff_t off = reinterpret_cast<const char*>(src) - reinterpret_cast<const char*>(pr->arena[pr->rank]);
+  GRAND_REQUIRE(off >= 0, GRAND_EINVAL, "peer_push_rows: src does not lie in the arena");
+  PeerPtrs pp;
+  for (int p = 0; p < GRAND_MAX_PEERS; ++p)
+    pp.out[p] = p < pr->world ? reinterpret_cast<float*>(reinterpret_cast<char*>(pr->arena[p]) + off) : nullptr;
+  const long long n_items = (long long)pr->n_push * (width >> 2);
+  long long blocks = (n_items + 255) / 256;
+  const long long cap = (long long)num_sms() * 8;
+  if (blocks > cap) blocks = cap;
+  peer_push_rows_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+      src, pr->n_push, width, pr->push_src, reinterpret_cast<const int2*>(pr->push_dst), pp);
+  GRAND_CUDA_OK(cudaGetLastError());
+  count_launch();
+  return GRAND_OK;
+}
+
+int grand_peer_barrier(const grand_peers* pr, void* stream) {
+  int rc;
+  if ((rc = check_peers(pr)) != GRAND_OK) return rc;
+  if (pr->world == 1) return GRAND_OK;
+  BarrierArgs b;
+  b.world = pr->world; b.rank = pr->rank;
+  for (int p = 0; p < GRAND_MAX_PEERS; ++p)
+    b.flags[p] = p < pr->world ? reinterpret_cast<int*>(reinterpret_cast<char*>(pr->arena[p]) + pr->flags_offset) : nullptr;
+  b.epoch = b.flags[pr->rank] + GRAND_MAX_PEERS;
+  b.error = b.epoch + 1;
+  peer_barrier_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(b);
+  GRAND_CUDA_OK(cudaGetLastError());
+  count_launch();
+  return GRAND_OK;
+}
+
+int grand_peer_error(const grand_peers* pr, int32_t* error_out) {
+  int rc;
+  if ((rc = check_peers(pr)) != GRAND_OK) return rc;
+  GRAND_REQUIRE(error_out != nullptr, GRAND_EINVAL, "peer_error: null argument");
+  const char* flags = reinterpret_cast<const char*>(pr->arena[pr->rank]) + pr->flags_offset;
+  GRAND_CUDA_OK(cudaMemcpy(error_out, flags + (GRAND_MAX_PEERS + 1) * sizeof(int32_t), sizeof(int32_t), cudaMemcpyDeviceToHost));
+  return GRAND_OK;
+}
+
+// Fixed-grid integration on a node partition: same stage algebra as grand_integrate_fixed below.
+int grand_integrate_fixed_sharded(const grand_graph* g, const grand_attention* a, const grand_workspace* ws,
+                                  const grand_epilogue* residual, int32_t method, const float* dt, int32_t n_steps,
+                                  float* y, float* yb, float* yc, float* k1, float* k2, float* k3, float* const* k_bufs,
+                                  int32_t* k_toggle, const grand_peers* pr, void* stream_) {
+  int rc;
+  if ((rc = check_peers(pr)) != GRAND_OK) return rc;
+  GRAND_REQUIRE(g && a && ws && residual && dt && y && yb && yc && k_bufs && k_bufs[0] && k_bufs[1] && k_toggle && n_steps >= 0,
+                GRAND_EINVAL, "integrate_fixed_sharded: null argument");
+  GRAND_REQUIRE(method == GRAND_EULER || method == GRAND_MIDPOINT || method == GRAND_RK4, GRAND_EINVAL,
+                "integrate_fixed_sharded: unknown method %d", method);
+  GRAND_REQUIRE(method != GRAND_RK4 || (k1 && k2 && k3), GRAND_EINVAL, "integrate_fixed_sharded: rk4 needs k1..k3");
+  cudaStream_t stream = (cudaStream_t)stream_;
+  const int d = a->d;
+  const int ad_eff = a->score_type == GRAND_SCORE_EXP_KERNEL2 ? 2 * a->ad : a->ad;
+  grand_workspace wsx = *ws;
+
+  // first stage input: own rows of y -> the peers' halos (every later stage input is delivered by the edge kernel's epilogue)
+  if ((rc = grand_peer_push_rows(pr, y, g->n_rows, d, stream_)) != GRAND_OK) return rc;
+
+  auto eval = [&](const float* x, grand_epilogue& ep) -> int {
+    ep.alpha_train = residual->alpha_train;
+    ep.beta_train = residual->beta_train;
+    ep.x0 = residual->x0;
+    ep.no_alpha_sigmoid = residual->no_alpha_sigmoid;
+    ep.peers = pr;
+    float* kb = k_bufs[*k_toggle & 1];
+    *k_toggle ^= 1;
+    wsx.k = kb;
+    int r;
+    if ((r = launch_project_qk(x, g->n_rows, g->n_rows, d, a->wq, a->bq, a->wk, a->bk, ad_eff, wsx.q, kb, stream)) != GRAND_OK)
+      return r;
+    if ((r = grand_peer_push_rows(pr, kb, g->n_rows, ad_eff, stream_)) != GRAND_OK) return r;
+    if ((r = grand_peer_barrier(pr, stream_)) != GRAND_OK) return r;
+    return rhs_attention_impl(g, a, x, &wsx, &ep, false, stream);
+  };
+
+  float* cur = y;
+  float* nxt = yc;
+  for (int s = 0; s < n_steps; ++s) {
+    const float h = dt[s];
+    grand_epilogue ep;
+    memset(&ep, 0, sizeof(ep));
+    if (method == GRAND_EULER) {
+      ep.y_out = nxt; ep.coef_f = h; ep.n_terms = 1; ep.term[0] = cur; ep.coef[0] = 1.f;
+      if ((rc = eval(cur, ep)) != GRAND_OK) return rc;
+    } else if (method == GRAND_MIDPOINT) {
+      ep.y_out = yb; ep.coef_f = 0.5f * h; ep.n_terms = 1; ep.term[0] = cur; ep.coef[0] = 1.f;
+      if ((rc = eval(cur, ep)) != GRAND_OK) return rc;
+      memset(&ep, 0, sizeof(ep));
+      ep.y_out = nxt; ep.coef_f = h; ep.n_terms = 1; ep.term[0] = cur; ep.coef[0] = 1.f;
+      if ((rc = eval(yb, ep)) != GRAND_OK) return rc;
+    } else {
+      const float third = 1.f / 3.f;
+      ep.f_out = k1; ep.y_out = yb; ep.coef_f = h * third; ep.n_terms = 1; ep.term[0] = cur; ep.coef[0] = 1.f;
+      if ((rc = eval(cur, ep)) != GRAND_OK) return rc;
+      memset(&ep, 0, sizeof(ep));
+      ep.f_out = k2; ep.y_out = nxt; ep.coef_f = h; ep.n_terms = 2;
+      ep.term[0] = cur; ep.coef[0] = 1.f; ep.term[1] = k1; ep.coef[1] = -h * third;
+      if ((rc = eval(yb, ep)) != GRAND_OK) return rc;
+      memset(&ep, 0, sizeof(ep));
+      ep.f_out = k3; ep.y_out = yb; ep.coef_f = h; ep.n_terms = 3;
+      ep.term[0] = cur; ep.coef[0] = 1.f; ep.term[1] = k1; ep.coef[1] = h; ep.term[2] = k2; ep.coef[2] = -h;
+      if ((rc = eval(nxt, ep)) != GRAND_OK) return rc;
+      memset(&ep, 0, sizeof(ep));
+      ep.y_out = nxt; ep.coef_f = h * 0.125f; ep.n_terms = 4;
+      ep.term[0] = cur; ep.coef[0] = 1.f; ep.term[1] = k1; ep.coef[1] = h * 0.125f;
+      ep.term[2] = k2; ep.coef[2] = 3.f * h * 0.125f; ep.term[3] = k3; ep.coef[3] = 3.f * h * 0.125f;
+      if ((rc = eval(yb, ep)) != GRAND_OK) return rc;
+    }
+    float* tmp = cur; cur = nxt; nxt = tmp;
+  }
+  // every rank must be done READING the halos of this integration before anybody starts delivering the next one's
+  if ((rc = grand_peer_barrier(pr, stream_)) != GRAND_OK) return rc;
+  if (cur != y && n_steps > 0) {
+    GRAND_CUDA_OK(cudaMemcpyAsync(y, cur, (size_t)g->n_rows * d * sizeof(float), cudaMemcpyDeviceToDevice, stream));
+    count_launch();
+  }
   return GRAND_OK;
 }
 

@@ -45,6 +45,13 @@ struct EpiView {
   const float* term[GRAND_MAX_TERMS];
 };
 
+// delivery of finished y_out rows into the halo of the peers that reference them (node-partitioned multi-GPU)
+struct PushView {
+  const int* ptr;                    // [n_rows + 1] or null
+  const int2* dst;                   // (peer, destination row)
+  float* out[GRAND_MAX_PEERS];       // y_out as seen through every peer's arena mapping
+};
+
 struct RhsArgs {
   GraphView g;
   AttnView a;          // MODE_FUSED / MODE_PRECOMP
@@ -64,6 +71,7 @@ struct RhsArgs {
   float* lrow_stats;         // [n_lunits, H, 2] softmax (max, sum-exp) of every long-row segment (rhs_stream.cu pre-pass)
   float* lpartial;           // [n_lunits, max(H,1), d] partial sums of the long-row segments (per head in MODE_FUSED)
   int* lcounter;             // [n_lrows] arrival counters (atomicInc wraps them back to zero)
+  PushView push;
   int l2_hints;              // bit 0: evict_last on the gathers, bit 1: evict_first on the streams
   int tile_begin, tile_end;  // window range of this launch (chunk tiles and packed windows may go to different streams)
 };

@@ -173,6 +173,22 @@ static EpiView view(const grand_epilogue* ep) {
   return v;
 }
 
+// delivery of y_out rows to the peers: y_out as every peer maps it = peer arena + (y_out - own arena)
+static int fill_push(const grand_epilogue* ep, PushView* out) {
+  memset(out, 0, sizeof(*out));
+  const grand_peers* pr = ep->peers;
+  if (pr == nullptr || ep->y_out == nullptr) return GRAND_OK;
+  GRAND_REQUIRE(pr->world >= 1 && pr->world <= GRAND_MAX_PEERS && pr->rank >= 0 && pr->rank < pr->world, GRAND_EINVAL,
+                "peers: world %d rank %d", pr->world, pr->rank);
+  GRAND_REQUIRE(pr->push_ptr != nullptr && pr->push_dst != nullptr, GRAND_EINVAL, "peers: null push lists");
+  const ptrdiff_t off = reinterpret_cast<const char*>(ep->y_out) - reinterpret_cast<const char*>(pr->arena[pr->rank]);
+  GRAND_REQUIRE(off >= 0, GRAND_EINVAL, "peers: y_out does not lie in the arena");
+  out->ptr = pr->push_ptr;
+  out->dst = reinterpret_cast<const int2*>(pr->push_dst);
+  for (int p = 0; p < pr->world; ++p) out->out[p] = reinterpret_cast<float*>(reinterpret_cast<char*>(pr->arena[p]) + off);
+  return GRAND_OK;
+}
+
 static int check_epilogue(const grand_epilogue* ep) {
   GRAND_REQUIRE(ep != nullptr && ep->alpha_train != nullptr, GRAND_EINVAL, "epilogue: alpha_train is null");
   GRAND_REQUIRE(ep->x0 == nullptr || ep->beta_train != nullptr, GRAND_EINVAL, "epilogue: x0 without beta_train");
@@ -311,9 +327,12 @@ int rhs_attention_impl(const grand_graph* g, const grand_attention* a, const flo
   A.split_stats = ws->split_stats; A.row_stats = ws->row_stats; A.split_partial = ws->split_partial;
   A.split_counter = ws->split_counter;
   A.lrow_stats = ws->lrow_stats; A.lpartial = ws->lpartial; A.lcounter = ws->lcounter;
+  if ((rc = fill_push(ep, &A.push)) != GRAND_OK) return rc;
   A.tile_begin = 0;
   A.tile_end = g->n_tiles;
   const bool stream_ok = stream_kernel_ok(A);
+  GRAND_REQUIRE(A.push.ptr == nullptr || stream_ok, GRAND_EUNSUPPORTED,
+                "the peer push needs the persistent edge kernel (16-byte rows)");
   GRAND_REQUIRE(stream_ok || g->n_split_tiles == 0 || (ws->split_partial && ws->split_counter), GRAND_EINVAL,
                 "graph has split rows: workspace split_partial / split_counter are null");
   if (project) {
@@ -374,6 +393,7 @@ int rhs_attention_backward_host(const grand_graph* g, const grand_attention* a, 
   A.split_stats = ws->split_stats; A.row_stats = ws->row_stats; A.split_partial = ws->split_partial;
   A.split_counter = ws->split_counter;
   A.lrow_stats = nullptr; A.lpartial = nullptr; A.lcounter = nullptr;
+  memset(&A.push, 0, sizeof(A.push));
   rc = launch_project_qk(x, g->n_rows, g->n_cols, a->d, a->wq, a->bq, a->wk, a->bk, A.a.ad_eff, ws->q, ws->k, stream);
   if (rc != GRAND_OK) return rc;
   if (g->n_split_tiles > 0) {
@@ -405,6 +425,7 @@ int rhs_laplacian_impl(const grand_graph* g, int d, const float* x, const float*
   A.split_partial = ws ? ws->split_partial : nullptr;
   A.split_counter = ws ? ws->split_counter : nullptr;
   A.lrow_stats = nullptr;
+  if ((rc = fill_push(ep, &A.push)) != GRAND_OK) return rc;
   A.lpartial = ws ? ws->lpartial : nullptr;
   A.lcounter = ws ? ws->lcounter : nullptr;
   if (stream_kernel_ok(A)) return launch_stream_mode(MODE_WEIGHT, A, stream);

@@ -216,6 +216,16 @@ __device__ __forceinline__ void epi_finish(const RhsArgs& A, unsigned rowoff, in
       }
       // y_out is the next stage's gather source: keep it cacheable
       *reinterpret_cast<float4*>(A.ep.y_out + o) = y;
+      if (A.push.ptr != nullptr) {
+        // node partition: the same row straight into the halo of every peer whose edges reference it (plain stores over
+        // NVLink through the peer's arena mapping); the exchange rides along with the rest of the launch
+        const int row = rowoff / (unsigned)A.d;
+        const int pb = __ldg(A.push.ptr + row), pe = __ldg(A.push.ptr + row + 1);
+        for (int t = pb; t < pe; ++t) {
+          const int2 dst = __ldg(A.push.dst + t);
+          *reinterpret_cast<float4*>(A.push.out[dst.x] + (size_t)dst.y * A.d + c) = y;
+        }
+      }
     }
   }
 }
@@ -611,6 +621,7 @@ rhs_stream_kernel(const __grid_constant__ RhsArgs A) {
     h4 = h4n;
     rec = recn;
   }
+  if (A.push.ptr != nullptr) __threadfence_system();     // every row this thread delivered to a peer is visible there
 }
 
 // ---- launchers ------------------------------------------------------------------------------------------------------------

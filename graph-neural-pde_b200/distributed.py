@@ -3,13 +3,22 @@
 One process per GPU (`torch.distributed`, NCCL).  Rows of the state X are split into P contiguous ranges balanced by
 edge count; rank p owns the CSR rows (all in-edges of its query nodes), so the attention softmax (attention_norm_idx
 0) and the aggregation are local.  What is not local are the neighbour rows X_j owned by other ranks -- the HALO.
-Per RHS evaluation:
+Every state / K buffer is laid out [own rows | halo rows grouped by owner].
 
-    1. pack the own rows other ranks need (grand_pack_rows) and exchange them (NCCL all-to-all-v; the receive buffer
-       IS the halo section of the local state, laid out [own rows | halo rows grouped by owner]),
-    2. project Q for the own rows and K for own + halo rows (K_j of a halo row is recomputed locally: ad*d MACs
-       instead of shipping ad more floats),
-    3. run the fused edge kernel over the local graph; its epilogue writes the next stage's own rows.
+Transport 'peer' (default): all buffers with a halo live in one device allocation per rank, the ARENA, mapped into
+every other rank's address space (CUDA IPC over NVLink).  Per RHS evaluation, all of it kernels on ONE stream (so the
+whole integration is captured into a CUDA Graph), no NCCL on the data path:
+
+    1. project Q, K for the own rows,
+    2. grand_peer_push_rows: the K rows other ranks reference go straight into their K halo (plain stores through
+       the peer mapping),
+    3. grand_peer_barrier: one small kernel, release / acquire flags in peer memory,
+    4. the fused edge kernel over the local graph; its epilogue writes the next stage's own rows AND stores every
+       row a peer references into that peer's halo as it is produced, so the exchange of stage s+1's input rides
+       along with stage s's compute.
+
+Transport 'nccl' (round-1 path, kept as the fallback for boxes without peer access and as the A/B): pack the boundary
+rows (grand_pack_rows), two NCCL all-to-all-v (X rows, K rows) into the halo sections, then the edge kernel.
 
 The reference has no distributed path at all; this is new design.  Everything that decides WHO owns
 WHAT is plain index arithmetic and is exercised on CPU with gloo (tests/test_distributed_cpu.py).
@@ -63,8 +72,10 @@ class Partition:
       cols = np.unique(col[mine])
       return cols[(cols < self.bounds[p]) | (cols >= self.bounds[p + 1])]
 
+    halos = [needs(p) for p in range(world)]
+    self.n_cols_all = [self.bounds[p + 1] - self.bounds[p] + len(halos[p]) for p in range(world)]
     # my halo, grouped by owner (np.unique is sorted and owners are contiguous ranges => already grouped)
-    halo = needs(rank)
+    halo = halos[rank]
     self.halo_global = halo
     self.n_halo = len(halo)
     halo_owner = owner_of[halo] if len(halo) else np.empty(0, dtype=np.int64)
@@ -75,11 +86,29 @@ class Partition:
       if p == rank:
         self.send_counts.append(0)
         continue
-      want = needs(p)
+      want = halos[p]
       want = want[(want >= self.r0) & (want < self.r1)]
       send_idx.append(want - self.r0)
       self.send_counts.append(len(want))
     self.send_index = np.concatenate(send_idx) if send_idx else np.empty(0, dtype=np.int64)
+    # push lists (transport 'peer'): for every own row, the (peer, row in the peer's buffers) pairs that hold it as a
+    # halo row; a peer's halo is sorted by global id, so the destination is n_own(peer) + its rank in that halo
+    rows, peers_, dests = [], [], []
+    for p in range(world):
+      if p == rank:
+        continue
+      pos = np.nonzero((halos[p] >= self.r0) & (halos[p] < self.r1))[0]
+      rows.append(halos[p][pos] - self.r0)
+      peers_.append(np.full(len(pos), p, dtype=np.int64))
+      dests.append(self.bounds[p + 1] - self.bounds[p] + pos)
+    rows = np.concatenate(rows) if rows else np.empty(0, dtype=np.int64)
+    peers_ = np.concatenate(peers_) if peers_ else np.empty(0, dtype=np.int64)
+    dests = np.concatenate(dests) if dests else np.empty(0, dtype=np.int64)
+    order = np.argsort(rows, kind='stable')
+    self.push_ptr = np.zeros(self.n_own + 1, dtype=np.int64)
+    np.cumsum(np.bincount(rows, minlength=self.n_own), out=self.push_ptr[1:])
+    self.push_dst = np.stack([peers_[order], dests[order]], axis=1) if len(rows) else np.empty((0, 2), dtype=np.int64)
+    self.push_src = rows[order]
 
     # local graph: rows -> [0, n_own), cols -> own index or n_own + position in halo
     mine = (row >= self.r0) & (row < self.r1)
@@ -124,23 +153,90 @@ def exchange_halo(send_buf, recv_buf, send_counts, recv_counts, group=None):
       req.wait()
 
 
+class _DevicePointer:
+  """Zero-copy torch view of raw device memory (torch.as_tensor reads __cuda_array_interface__)."""
+
+  def __init__(self, ptr, shape, typestr):
+    self.__cuda_array_interface__ = {'shape': tuple(shape), 'typestr': typestr, 'data': (int(ptr), False), 'version': 2}
+
+
+def _align(v, a=256):
+  return (v + a - 1) // a * a
+
+
+class PeerArena:
+  """One cudaMalloc per rank holding every buffer that has a halo section -- three state buffers [n_cols_max, d], two
+  K buffers [n_cols_max, ad] -- and the barrier words, at the SAME byte offsets on every rank, exported with CUDA IPC
+  and opened by every other rank (all_gather_object of the 64-byte handles).  `n_cols_max` = the largest
+  own + halo row count of any rank, so that a buffer's offset does not depend on the rank."""
+
+  STATE_NAMES = ('y', 'yb', 'yc')
+
+  def __init__(self, n_cols_max, d, ad, device, group=None):
+    self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+    self.device = torch.device(device)
+    self.n_cols_max, self.d, self.ad = int(n_cols_max), int(d), int(ad)
+    off, self.offsets = 0, {}
+    for name in self.STATE_NAMES:
+      self.offsets[name] = off
+      off = _align(off + self.n_cols_max * d * 4)
+    for name in ('k0', 'k1'):
+      self.offsets[name] = off
+      off = _align(off + self.n_cols_max * ad * 4)
+    self.flags_offset = off
+    off = _align(off + (N.GRAND_MAX_PEERS + 2) * 4)
+    self.bytes = off
+    lib = N.lib()
+    base = C.c_void_p()
+    N.check(lib.grand_peer_alloc(self.bytes, C.byref(base)))
+    self.base = base.value
+    handle = (C.c_char * 64)()
+    N.check(lib.grand_peer_export(self.base, handle))
+    handles = [None] * self.world
+    dist.all_gather_object(handles, bytes(handle.raw), group=group)
+    self.peer_base = []
+    for p in range(self.world):
+      if p == self.rank:
+        self.peer_base.append(self.base)
+      else:
+        ptr = C.c_void_p()
+        N.check(lib.grand_peer_open((C.c_char * 64).from_buffer_copy(handles[p]), C.byref(ptr)))
+        self.peer_base.append(ptr.value)
+    dist.barrier(group=group)          # nobody touches a peer's arena before every rank has zeroed and mapped its own
+
+  def tensor(self, name, rows, width):
+    return torch.as_tensor(_DevicePointer(self.base + self.offsets[name], (rows, width), '<f4'), device=self.device)
+
+  def close(self):
+    lib = N.lib()
+    for p, ptr in enumerate(self.peer_base):
+      if p != self.rank and ptr:
+        lib.grand_peer_close(ptr)
+    if self.base:
+      lib.grand_peer_free(self.base)
+    self.peer_base, self.base = [], None
+
+
 class ShardedTransformerRHS:
   """GRAND-nl on a node partition: the device side of one rank.  `func` is this package's ODEFuncTransformerAtt built
   over the FULL graph (its parameters are replicated on every rank, like DDP); this object owns the rank's local plan,
-  state buffers and the stage driver."""
+  state buffers and the stage driver.  transport: 'peer' (NVLink stores through IPC-mapped arenas, CUDA-Graph replay)
+  or 'nccl' (pack + all-to-all-v, host-driven)."""
 
-  def __init__(self, func, num_nodes, device, group=None):
+  def __init__(self, func, num_nodes, device, group=None, transport=None):
+    import os
     self.func = func
     self.group = group
     self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
     self.device = torch.device(device)
+    self.transport = transport or os.environ.get('GRAND_TRANSPORT', 'peer')
+    if dist.get_backend(group) != 'nccl':
+      self.transport = 'nccl'          # CPU / gloo tests exercise the host logic through the exchange path
     self.part = Partition(func.edge_index, num_nodes, self.world, self.rank)
     p = self.part
     self.d = int(func.in_features)
     self.plan = GraphPlan(p.local_edge_index, num_nodes=p.n_own, device=self.device, num_cols=p.n_cols)
     self.engine = RhsEngine(self.plan, self.d)
-    self.send_index = torch.from_numpy(p.send_index).to(self.device, torch.int32)
-    self.send_buf = torch.empty((max(len(p.send_index), 1), self.d), dtype=torch.float32, device=self.device)
     opt = func.opt
     if not (opt['attention_norm_idx'] == 0 and not opt['square_plus']):
       raise NotImplementedError('the sharded path needs row-local normalisation (attention_norm_idx 0, softmax); '
@@ -150,17 +246,58 @@ class ShardedTransformerRHS:
     self.spec = func.multihead_att_layer.spec(self.engine)
     self.ws = self.engine.workspace(self.spec)
     ad = self.spec.ad_eff
-    self.send_buf_k = torch.empty((max(len(p.send_index), 1), ad), dtype=torch.float32, device=self.device)
-    # [n_cols, ad] view of the engine's K workspace: its halo section is a receive buffer of the exchange
-    self.k_view = self.engine._ws_keep['k'][:p.n_cols * ad].view(p.n_cols, ad)
     self._bufs = {}
     self._graphs = {}
+    self.arena = None
+    if self.transport == 'peer':
+      if self.d % 4 or ad % 4:
+        raise NotImplementedError('the peer transport needs 16-byte rows (state width and attention_dim % 4 == 0)')
+      self.arena = PeerArena(max(p.n_cols_all), self.d, ad, self.device, group)
+      for name in PeerArena.STATE_NAMES:
+        self._bufs[name] = self.arena.tensor(name, p.n_cols, self.d)
+      self.k_bufs = [self.arena.tensor('k0', p.n_cols, ad), self.arena.tensor('k1', p.n_cols, ad)]
+      self.k_ptrs = (C.c_void_p * 2)(self.k_bufs[0].data_ptr(), self.k_bufs[1].data_ptr())
+      self.k_toggle = C.c_int32(0)
+      self.push_ptr = torch.from_numpy(p.push_ptr).to(self.device, torch.int32)
+      self.push_dst = torch.from_numpy(np.ascontiguousarray(p.push_dst)).to(self.device, torch.int32)
+      pr = N.GrandPeers()
+      pr.world, pr.rank = self.world, self.rank
+      for q, ptr in enumerate(self.arena.peer_base):
+        pr.arena[q] = ptr
+      pr.flags_offset = self.arena.flags_offset
+      self.push_src = torch.from_numpy(np.ascontiguousarray(p.push_src)).to(self.device, torch.int32)
+      pr.push_ptr, pr.push_dst = self.push_ptr.data_ptr(), self.push_dst.data_ptr()
+      pr.push_src, pr.n_push = self.push_src.data_ptr(), int(len(p.push_src))
+      self.peers = pr
+    else:
+      self.send_index = torch.from_numpy(p.send_index).to(self.device, torch.int32)
+      self.send_buf = torch.empty((max(len(p.send_index), 1), self.d), dtype=torch.float32, device=self.device)
+      self.send_buf_k = torch.empty((max(len(p.send_index), 1), ad), dtype=torch.float32, device=self.device)
+      # [n_cols, ad] view of the engine's K workspace: its halo section is a receive buffer of the exchange
+      self.k_view = self.engine._ws_keep['k'][:p.n_cols * ad].view(p.n_cols, ad)
+
+  def close(self):
+    self._graphs.clear()
+    if self.arena is not None:
+      torch.cuda.synchronize(self.device)
+      self.arena.close()
+      self.arena = None
+
+  def check_barriers(self):
+    """Raises if a cross-GPU barrier timed out (a peer never arrived); host-synchronous."""
+    if self.arena is None:
+      return
+    err = C.c_int32(0)
+    N.check(N.lib().grand_peer_error(C.byref(self.peers), C.byref(err)))
+    if err.value != 0:
+      raise N.GrandError('rank %d: a peer did not arrive at barrier epoch %d' % (self.rank, err.value))
 
   # ---- buffers: [n_cols, d] with the own rows first ---------------------------------------------------------
   def buffer(self, name):
     t = self._bufs.get(name)
     if t is None:
-      t = torch.zeros((self.part.n_cols, self.d), dtype=torch.float32, device=self.device)
+      rows = self.part.n_own if (self.arena is not None and name not in PeerArena.STATE_NAMES) else self.part.n_cols
+      t = torch.zeros((rows, self.d), dtype=torch.float32, device=self.device)
       self._bufs[name] = t
     return t
 
@@ -173,7 +310,7 @@ class ShardedTransformerRHS:
     self.own(buf).copy_(x_global[self.part.r0:self.part.r1].to(self.device))
     return buf
 
-  # ---- one RHS evaluation -------------------------------------------------------------------------------------
+  # ---- one RHS evaluation, transport 'nccl' --------------------------------------------------------------------
   def rhs(self, x, ep):
     """x: [n_cols, d] buffer whose own rows are current.  Projects the own rows (Q, K), ships the boundary rows of X
     AND of K to the ranks that reference them (K_j travels with X_j: ad floats more per row instead of re-projecting
@@ -202,9 +339,19 @@ class ShardedTransformerRHS:
   # ---- fixed-grid rk4 (3/8 rule), euler, midpoint: same stage algebra as grand_integrate_fixed ---------------
   def integrate_fixed(self, y, x0, method, dts):
     """y: [n_cols, d] buffer, own rows = y(t0); returns the buffer holding y(t_end) (own rows)."""
+    per_step = {'euler': 1, 'midpoint': 2, 'rk4': 4}[method]
+    if self.transport == 'peer':
+      yb, yc = self.buffer('yb'), self.buffer('yc')
+      k1, k2, k3 = (self.buffer(n) for n in ('k1', 'k2', 'k3'))
+      dt_arr = (C.c_float * len(dts))(*dts)
+      self.func._bump_nfe(per_step * len(dts))
+      N.check(N.lib().grand_integrate_fixed_sharded(
+        C.byref(self.plan.struct()), C.byref(self.spec.struct), C.byref(self.ws), C.byref(self.epilogue(x0)),
+        N.METHODS[method], dt_arr, len(dts), y.data_ptr(), yb.data_ptr(), yc.data_ptr(), k1.data_ptr(), k2.data_ptr(),
+        k3.data_ptr(), self.k_ptrs, C.byref(self.k_toggle), C.byref(self.peers), N.current_stream(self.device)))
+      return y
     yb, yc, k1, k2, k3 = (self.buffer(n) for n in ('yb', 'yc', 'k1', 'k2', 'k3'))
     cur, nxt = y, yc
-    per_step = {'euler': 1, 'midpoint': 2, 'rk4': 4}[method]
     for h in dts:
       self.func._bump_nfe(per_step)
       if method == 'euler':
@@ -222,36 +369,43 @@ class ShardedTransformerRHS:
       cur, nxt = nxt, cur
     return cur
 
-  def forward_block(self, x_own, x0_own, opt, use_graph=False):
+  def forward_block(self, x_own, x0_own, opt, use_graph=None):
     """Block forward over [0, T] for this rank's rows: returns z for the own rows (a view of a persistent buffer).
-    `use_graph=True` captures the whole stage loop -- kernels AND the NCCL exchanges -- into one CUDA Graph on the
-    second call and replays it afterwards.  EXPERIMENTAL and off by default: the first attempt on 4 x B200 did not
-    return within 15 minutes (capture of the all-to-all never completed), so the stage loop is host-driven for now."""
+    Transport 'peer': the whole integration -- projections, pushes, barriers, edge kernels -- is ONE CUDA Graph,
+    captured on the second call (every rank must replay it: the barriers inside wait for all of them).  Transport
+    'nccl' stays host-driven (capturing its all-to-alls never completed on 4 x B200 in round 1)."""
     dts, _ = fixed_grid_dts(0.0, opt['time'], opt['step_size'])
     method = opt['method']
     y = self.buffer('y')
     self.own(y).copy_(x_own)
     x0 = self.buffer('x0')
     self.own(x0).copy_(x0_own)
-    if not use_graph:
+    if use_graph is None:
+      use_graph = self.transport == 'peer'
+    if not use_graph or self.transport != 'peer':
       return self.own(self.integrate_fixed(y, x0, method, dts))
     key = (method, tuple(dts))
     entry = self._graphs.get(key)
-    if entry is None:                       # first call: eager (warms up NCCL and the kernels)
+    if entry is None:                       # first call: eager (module load, attribute set-up)
       out = self.integrate_fixed(y, x0, method, dts)
-      self._graphs[key] = ('warm', out)
+      self._graphs[key] = ('warm',)
       return self.own(out)
     if entry[0] == 'warm':
       saved = self.own(y).clone()
       torch.cuda.synchronize(self.device)
+      dist.barrier(group=self.group)
       graph = torch.cuda.CUDAGraph()
-      nfe = self.func.nfe
+      nfe, toggle = self.func.nfe, self.k_toggle.value
       with torch.cuda.graph(graph):
-        out = self.integrate_fixed(y, x0, method, dts)
+        self.integrate_fixed(y, x0, method, dts)
       self.func.nfe = nfe
+      per_forward = {'euler': 1, 'midpoint': 2, 'rk4': 4}[method] * len(dts)
+      if per_forward % 2:                   # an odd number of evaluations would flip the K buffer between replays
+        raise NotImplementedError('graph replay of the sharded path needs an even number of RHS evaluations per forward')
+      self.k_toggle.value = toggle
       self.own(y).copy_(saved)
-      entry = ('graph', out, graph)
+      entry = ('graph', graph)
       self._graphs[key] = entry
     self.func._bump_nfe({'euler': 1, 'midpoint': 2, 'rk4': 4}[method] * len(dts))
-    entry[2].replay()
-    return self.own(entry[1])
+    entry[1].replay()
+    return self.own(y)

@@ -38,6 +38,7 @@ extern "C" {
 #define GRAND_MAX_PACKED_ROWS 8  /* whole rows packed into one window: at most this many */
 #define GRAND_MAX_HEADS 8
 #define GRAND_MAX_TERMS 8
+#define GRAND_MAX_PEERS 8        /* GPUs of one NVLink / NVSwitch domain that share a node partition */
 
 /* attention_type, reference src/function_transformer_attention.py:193-206 */
 enum grand_score_type {
@@ -115,6 +116,26 @@ typedef struct grand_attention {
 } grand_attention;
 
 /*
+ * Node-partitioned multi-GPU (new design; the reference has no distributed path).  Every rank owns a
+ * contiguous range of rows; the rows of other ranks that its edges reference -- the HALO -- live behind its own rows in
+ * every state / K buffer ([own rows | halo rows grouped by owner]).  All such buffers of a rank sit in ONE device
+ * allocation, the ARENA, laid out identically on every rank and mapped into every other rank's address space (CUDA
+ * IPC over NVLink): a rank delivers a row by plain stores through arena[peer] at the same byte offset the buffer has
+ * in its own arena.  push_ptr / push_dst list, for every own row, which peers hold it in their halo and at which row.
+ */
+typedef struct grand_peers {
+  int32_t world;               /* ranks (<= GRAND_MAX_PEERS)                                          */
+  int32_t rank;
+  void* arena[GRAND_MAX_PEERS];/* this process's mapping of every rank's arena; arena[rank] is its own */
+  int64_t flags_offset;        /* byte offset inside every arena of int32 flags[GRAND_MAX_PEERS] (arrivals, written by
+                                  the peers), int32 epoch (barrier counter), int32 error: zero at start  */
+  const int32_t* push_ptr;     /* [n_rows + 1]                                                        */
+  const int32_t* push_dst;     /* [push_ptr[n_rows], 2]: peer, destination row in the peer's buffers  */
+  const int32_t* push_src;     /* [push_ptr[n_rows]] own row of every push entry (the CSR above, flattened) */
+  int32_t n_push;              /* push_ptr[n_rows]                                                    */
+} grand_peers;
+
+/*
  * What happens to the RHS value f_i once a row is finished -- the residual of
  * reference src/function_transformer_attention.py:46-53 / src/function_laplacian_diffusion.py:43-51
  *     f = alpha (ax - x) [+ beta x0],  alpha = sigmoid(*alpha_train) unless no_alpha_sigmoid
@@ -132,6 +153,9 @@ typedef struct grand_epilogue {
   float coef_f;
   float coef[GRAND_MAX_TERMS];
   const float* term[GRAND_MAX_TERMS];
+  const grand_peers* peers;    /* or null.  Non-null: y_out lies in the arena and every finished row of it is ALSO
+                                  stored into the halo of the peers that reference it, from the same kernel, as the
+                                  row is produced (the exchange overlaps the rest of the launch)         */
 } grand_epilogue;
 
 /* caller-owned scratch; sizes from grand_workspace_sizes */
@@ -226,6 +250,33 @@ int grand_lincomb(int64_t n, int32_t n_terms, const float* const* term, const fl
  * *sumsq (caller zeroes it), err = sum_t coef[t] * k[t]   (torchdiffeq _compute_error_ratio with rms norm). */
 int grand_error_sumsq(int64_t n, int32_t n_terms, const float* const* k, const float* coef, const float* y0,
                       const float* y1, float atol, float rtol, double* sumsq, void* stream);
+
+/* ---- node-partitioned multi-GPU over peer-mapped memory (see grand_peers) ------------------------------------------
+ * Arena life cycle (the only entry points of this library that allocate): cudaMalloc / cudaIpcGetMemHandle /
+ * cudaIpcOpenMemHandle / cudaIpcCloseMemHandle / cudaFree.  `handle` is the 64-byte cudaIpcMemHandle_t. */
+int grand_peer_alloc(int64_t bytes, void** ptr);
+int grand_peer_free(void* ptr);
+int grand_peer_export(void* ptr, void* handle64);
+int grand_peer_open(const void* handle64, void** ptr);
+int grand_peer_close(void* ptr);
+/* Stores the own rows of `src` ([n_rows, width] inside the own arena, width % 4 == 0) into the halo sections of the
+ * peers that reference them (push lists of `peers`); one thread per (push entry, 16-byte piece), so every delivery is
+ * an independent load -> store.  Used for the K rows after the projection and for the first stage input. */
+int grand_peer_push_rows(const grand_peers* peers, const float* src, int32_t n_rows, int32_t width, void* stream);
+/* All ranks of `peers` wait for each other ON THE STREAM: bumps the local epoch, publishes it into every peer's flags
+ * (release, system scope) and spins until every peer's epoch has arrived (acquire).  Everything the peers stored
+ * before their barrier is visible afterwards.  A peer that does not arrive within ~2 s sets `error` instead of hanging
+ * the GPU (grand_peer_error reads it back after a synchronize). */
+int grand_peer_barrier(const grand_peers* peers, void* stream);
+/* HOST-synchronous read of the barrier error flag (0 = every barrier so far completed). */
+int grand_peer_error(const grand_peers* peers, int32_t* error_out);
+/* grand_integrate_fixed on a node partition: per evaluation  project own rows -> push K rows -> barrier -> edge kernel
+ * (its epilogue pushes the next stage's rows).  y / yb / yc and k_bufs[0..1] ([n_cols, d] / [n_cols, ad]) lie in the
+ * arena; k1..k3 ([n_rows, d]) are local.  *k_toggle selects the K buffer of the first evaluation and is updated. */
+int grand_integrate_fixed_sharded(const grand_graph* g, const grand_attention* a, const grand_workspace* ws,
+                                  const grand_epilogue* residual, int32_t method, const float* dt, int32_t n_steps,
+                                  float* y, float* yb, float* yc, float* k1, float* k2, float* k3, float* const* k_bufs,
+                                  int32_t* k_toggle, const grand_peers* peers, void* stream);
 
 /* HOST function (plain CPU code, no CUDA call): the sequential step of building a grand_graph -- greedy packing of
  * consecutive rows with <= tile in-edges into windows of <= tile edges and <= max_rows (<= GRAND_MAX_PACKED_ROWS) rows;

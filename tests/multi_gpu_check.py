@@ -45,14 +45,27 @@ def main():
     block.odefunc.beta_train.fill_(0.25)
   block.eval()
   xd = x.to(dev)
-  shard = ShardedTransformerRHS(block.odefunc, n, dev)
-  part = shard.part
   with torch.no_grad():
-    for _ in range(2):   # twice: persistent buffers must be reusable
-      z_shard = shard.forward_block(xd[part.r0:part.r1], xd[part.r0:part.r1], opt).clone()
     block.set_x0(xd)
     z_full = block(xd)
-  err_single = float((z_shard - z_full[part.r0:part.r1]).abs().max() / z_full.abs().max())
+  err_single = 0.0
+  for transport in ('peer', 'nccl'):
+    shard = ShardedTransformerRHS(block.odefunc, n, dev, transport=transport)
+    part = shard.part
+    with torch.no_grad():
+      for it in range(4):   # eager, capture + replay, replay, replay with another input: buffers and the graph are reusable
+        xin = xd if it < 3 else 0.5 * xd
+        z_shard = shard.forward_block(xin[part.r0:part.r1], xd[part.r0:part.r1], opt).clone()
+        if it == 2:
+          z_keep = z_shard
+    torch.cuda.synchronize()
+    shard.check_barriers()
+    err_t = float((z_keep - z_full[part.r0:part.r1]).abs().max() / z_full.abs().max())
+    print('rank %d transport %s: err vs single-GPU %.2e' % (rank, transport, err_t), flush=True)
+    err_single = max(err_single, err_t)
+    z_shard = z_keep
+    if transport == 'peer':
+      shard.close()
   # CPU oracle on rank 0 only (it is the slow leg)
   err_oracle = 0.0
   if rank == 0:

@@ -40,6 +40,32 @@ def test_partition_invariants():
         assert p.recv_counts[q.rank] == q.send_counts[p.rank]
 
 
+def test_push_lists_fill_every_halo():
+  """Transport 'peer': every rank stores its boundary rows straight into the peers' halo sections.  Replayed on the host:
+  after all ranks have pushed, every rank's [own | halo] buffer equals the global rows it references."""
+  import numpy as np
+  n = 500
+  ei = make_graph(n, 3000, max_degree=80, seed=3)
+  ei = torch.cat([ei, torch.stack([torch.arange(n), torch.arange(n)])], dim=1)
+  for world in (2, 3, 4, 8):
+    parts = [Partition(ei, n, world, r) for r in range(world)]
+    x = np.arange(n, dtype=np.float64)
+    bufs = [np.full(p.n_cols, -1.0) for p in parts]
+    for p in parts:
+      bufs[p.rank][:p.n_own] = x[p.r0:p.r1]
+      assert p.push_ptr[0] == 0 and p.push_ptr[-1] == len(p.push_dst) == sum(p.send_counts)
+      assert p.n_cols_all[p.rank] == p.n_cols and len(p.n_cols_all) == world
+    for p in parts:
+      for row in range(p.n_own):
+        for t in range(int(p.push_ptr[row]), int(p.push_ptr[row + 1])):
+          peer, dst = (int(v) for v in p.push_dst[t])
+          assert peer != p.rank and parts[peer].n_own <= dst < parts[peer].n_cols
+          assert bufs[peer][dst] == -1.0, 'a halo row is delivered exactly once'
+          bufs[peer][dst] = x[p.r0 + row]
+    for p in parts:
+      assert np.array_equal(bufs[p.rank], np.concatenate([x[p.r0:p.r1], x[p.halo_global]]))
+
+
 def test_balanced_ranges_handle_degenerate_inputs():
   assert balanced_row_ranges([0, 0, 0, 0], 2) == [0, 2, 4]
   b = balanced_row_ranges([1000, 1, 1, 1], 3)

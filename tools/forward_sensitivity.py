@@ -1,0 +1,54 @@
+"""How far apart do two fp32 evaluations of the SAME arxiv-scale forward (24 RHS evals) end up, and how far is each from
+an fp64 solution?  Compares: the GPU engine with two different work lists (seg_edges 256 vs 64 -> different summation
+orders), the fp32 CPU oracle and the fp64 CPU oracle.  Answers whether the 1e-5 bar is meaningful for the whole
+forward of this configuration or only per evaluation.   python tools/forward_sensitivity.py   (GPU box, ~2 min)"""
+import os
+import sys
+import time
+
+import torch
+
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), '..'))
+sys.path.insert(0, ROOT)
+import bench  # noqa: E402
+from graph_neural_pde_b200 import _native as N  # noqa: E402  (bench loaded the package)
+from oracle import grand_oracle as O  # noqa: E402
+
+dev = torch.device('cuda:0')
+
+
+def gpu_forward(seg):
+  N.GRAND_SEG_EDGES = seg
+  import graph_neural_pde_b200.graph_plan as GP
+  GP.GraphPlan.__init__.__defaults__ = GP.GraphPlan.__init__.__defaults__[:-1] + (seg,)
+  ds, opt, x, block = bench.make_block('ogbn-arxiv', dev)
+  xd = x.to(dev)
+  block.set_x0(xd)
+  with torch.no_grad():
+    z = block(xd).cpu()
+  return ds, opt, x, block, z
+
+
+ds, opt, x, block, z256 = gpu_forward(256)
+_, _, _, _, z64 = gpu_forward(64)
+n = ds.data.num_nodes
+state = {k: v.detach().cpu() for k, v in block.state_dict().items()}
+rel = lambda a, b: float((a.double() - b.double()).abs().max() / b.double().abs().max())
+print('GPU seg256 vs GPU seg64      %.3e' % rel(z256, z64), flush=True)
+torch.set_num_threads(16)
+t0 = time.time()
+f32 = bench.oracle_func(state, opt, ds.data.edge_index, n, x)
+with torch.no_grad():
+  w32 = O.block_forward(f32, x, opt['time'], opt)
+print('oracle fp32 forward %.0f s' % (time.time() - t0), flush=True)
+print('GPU seg256 vs oracle fp32    %.3e' % rel(z256, w32), flush=True)
+state64 = {k: v.double() for k, v in state.items()}
+f64 = bench.oracle_func(state64, opt, ds.data.edge_index, n, x.double())
+t0 = time.time()
+with torch.no_grad():
+  w64 = O.block_forward(f64, x.double(), opt['time'], opt)
+print('oracle fp64 forward %.0f s' % (time.time() - t0), flush=True)
+print('GPU seg256 vs oracle fp64    %.3e' % rel(z256, w64))
+print('GPU seg64  vs oracle fp64    %.3e' % rel(z64, w64))
+print('oracle fp32 vs oracle fp64   %.3e' % rel(w32, w64))
+# one-evaluation amplification: perturb x by 1e-7 relative and integrate again on the GPU
