@@ -118,9 +118,15 @@ def init_trained_like(block, seed=0):
   """'trained-like' parameters (SURVEY.md 8(d) regime ii): W ~ N(0, 1/d), alpha_train = beta_train = 0."""
   g = torch.Generator().manual_seed(seed)
   with torch.no_grad():
-    for p in block.parameters():
+    for name, p in block.named_parameters():
       if p.dim() == 2:
         p.copy_((torch.randn(p.shape, generator=g) / p.shape[1] ** 0.5).to(p.device))
+    # the Linear biases keep PyTorch's default law U(+-1/sqrt(fan_in)) (reference :122-126 leaves them alone) but are
+    # drawn from the seeded generator: every rank of a multi-GPU run, and every block of an A/B, gets the same values
+    for name, p in block.named_parameters():
+      if name.endswith('.bias') and p.dim() == 1:
+        fan_in = dict(block.named_parameters())[name[:-5] + '.weight'].shape[1]
+        p.copy_(((torch.rand(p.shape, generator=g) * 2 - 1) / fan_in ** 0.5).to(p.device))
 
 
 def make_block(name, device):

@@ -56,7 +56,18 @@ class GrandEpilogue(C.Structure):
               ('no_alpha_sigmoid', C.c_int32), ('n_terms', C.c_int32),
               ('f_out', C.c_void_p), ('y_out', C.c_void_p), ('coef_f', C.c_float),
               ('coef', C.c_float * GRAND_MAX_TERMS), ('term', C.c_void_p * GRAND_MAX_TERMS),
-              ('peers', C.POINTER(GrandPeers))]
+              ('peers', C.POINTER(GrandPeers)), ('coef_dev', C.c_void_p)]
+
+
+GRAND_DOPRI5_COEFS = 72
+
+
+class GrandDopri5State(C.Structure):
+  _fields_ = [('t', C.c_double), ('t_prev', C.c_double), ('dt', C.c_double), ('t_end', C.c_double),
+              ('acc', C.c_double * 3), ('h0', C.c_double), ('rtol', C.c_float), ('atol', C.c_float),
+              ('numel', C.c_int32), ('attempts', C.c_int32), ('accepted', C.c_int32), ('nfe', C.c_int32),
+              ('max_attempts', C.c_int32), ('accept', C.c_int32), ('have_interp', C.c_int32), ('status', C.c_int32),
+              ('coef', C.c_float * GRAND_DOPRI5_COEFS)]
 
 
 class GrandWorkspace(C.Structure):
@@ -103,6 +114,11 @@ SIGNATURES = {
                                                C.POINTER(GrandEpilogue), C.c_int32, c_float_p, C.c_int32, _P, _P, _P, _P,
                                                _P, _P, C.POINTER(C.c_void_p), C.POINTER(C.c_int32),
                                                C.POINTER(GrandPeers), _P]),
+  'grand_dopri5_create': (C.c_int, [C.POINTER(GrandGraph), C.POINTER(GrandAttention), _P, C.c_int32,
+                                     C.POINTER(GrandWorkspace), C.POINTER(GrandEpilogue), _P, _P, _P, _P, C.c_double,
+                                     C.c_double, C.c_float, C.c_float, C.c_int32, C.POINTER(C.c_void_p)]),
+  'grand_dopri5_launch': (C.c_int, [_P, _P]),
+  'grand_dopri5_destroy': (C.c_int, [_P]),
   'grand_plan_pack_rows': (C.c_int64, [_P, C.c_int64, C.c_int32, C.c_int32, _P, _P]),
 }
 

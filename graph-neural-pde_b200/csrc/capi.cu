@@ -44,15 +44,19 @@ struct LincombArgs {
   int n_terms;
   const float* term[GRAND_MAX_TERMS];
   float coef[GRAND_MAX_TERMS];
+  const float* coef_dev;    // or null: device [n_terms] overriding coef[] (dopri5 controller)
 };
 
 __global__ void __launch_bounds__(256) lincomb_kernel(int64_t n, LincombArgs a, float* __restrict__ y) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  float c[GRAND_MAX_TERMS];
+#pragma unroll
+  for (int t = 0; t < GRAND_MAX_TERMS; ++t) c[t] = t < a.n_terms ? (a.coef_dev != nullptr ? __ldg(a.coef_dev + t) : a.coef[t]) : 0.f;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
     float v = 0.f;
 #pragma unroll
     for (int t = 0; t < GRAND_MAX_TERMS; ++t)
-      if (t < a.n_terms) v = fmaf(a.coef[t], a.term[t][i], v);
+      if (t < a.n_terms) v = fmaf(c[t], a.term[t][i], v);
     y[i] = v;
   }
 }
@@ -61,6 +65,8 @@ struct ErrArgs {
   int n_terms;
   const float* k[GRAND_MAX_TERMS];
   float coef[GRAND_MAX_TERMS];
+  const float* coef_dev;    // or null
+  const float* tol_dev;     // or null: device (rtol, atol) pair... unused: tolerances are launch constants
 };
 
 __global__ void __launch_bounds__(256)
@@ -68,11 +74,14 @@ error_sumsq_kernel(int64_t n, ErrArgs a, const float* __restrict__ y0, const flo
                    float rtol, double* __restrict__ sumsq) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   double local = 0.0;
+  float c[GRAND_MAX_TERMS];
+#pragma unroll
+  for (int t = 0; t < GRAND_MAX_TERMS; ++t) c[t] = t < a.n_terms ? (a.coef_dev != nullptr ? __ldg(a.coef_dev + t) : a.coef[t]) : 0.f;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
     float err = 0.f;
 #pragma unroll
     for (int t = 0; t < GRAND_MAX_TERMS; ++t)
-      if (t < a.n_terms) err = fmaf(a.coef[t], a.k[t][i], err);
+      if (t < a.n_terms) err = fmaf(c[t], a.k[t][i], err);
     const float tol = atol + rtol * fmaxf(fabsf(y0[i]), fabsf(y1[i]));
     const float r = err / tol;
     local += (double)r * (double)r;
@@ -254,6 +263,7 @@ int grand_lincomb(int64_t n, int32_t n_terms, const float* const* term, const fl
   if (n == 0) return GRAND_OK;
   LincombArgs a;
   a.n_terms = n_terms;
+  a.coef_dev = nullptr;
   for (int t = 0; t < GRAND_MAX_TERMS; ++t) {
     a.term[t] = t < n_terms ? term[t] : nullptr;
     a.coef[t] = t < n_terms ? coef[t] : 0.f;
@@ -271,6 +281,8 @@ int grand_error_sumsq(int64_t n, int32_t n_terms, const float* const* k, const f
   if (n == 0) return GRAND_OK;
   ErrArgs a;
   a.n_terms = n_terms;
+  a.coef_dev = nullptr;
+  a.tol_dev = nullptr;
   for (int t = 0; t < GRAND_MAX_TERMS; ++t) {
     a.k[t] = t < n_terms ? k[t] : nullptr;
     a.coef[t] = t < n_terms ? coef[t] : 0.f;

@@ -43,7 +43,13 @@ struct EpiView {
   float coef_f;
   float coef[GRAND_MAX_TERMS];
   const float* term[GRAND_MAX_TERMS];
+  const float* coef_dev;   // or null: device [1 + GRAND_MAX_TERMS] overriding coef_f / coef[] (device-side step control)
 };
+// stage-combine coefficients as the kernel sees them: host values, or the device table of the dopri5 controller
+__device__ __forceinline__ float epi_coef_f(const EpiView& ep) { return ep.coef_dev != nullptr ? __ldg(ep.coef_dev) : ep.coef_f; }
+__device__ __forceinline__ float epi_coef(const EpiView& ep, int t) {
+  return ep.coef_dev != nullptr ? __ldg(ep.coef_dev + 1 + t) : ep.coef[t];
+}
 
 // delivery of finished y_out rows into the halo of the peers that reference them (node-partitioned multi-GPU)
 struct PushView {

@@ -170,6 +170,7 @@ static EpiView view(const grand_epilogue* ep) {
     v.coef[t] = t < ep->n_terms ? ep->coef[t] : 0.f;
     v.term[t] = t < ep->n_terms ? ep->term[t] : nullptr;
   }
+  v.coef_dev = ep->coef_dev;
   return v;
 }
 

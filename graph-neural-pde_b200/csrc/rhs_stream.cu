@@ -204,13 +204,14 @@ __device__ __forceinline__ void epi_finish(const RhsArgs& A, unsigned rowoff, in
     }
     if (A.ep.f_out != nullptr) st_stream4_hint(A.ep.f_out + o, f, pol_stream);
     if (A.ep.y_out != nullptr) {
-      float4 y = make_float4(A.ep.coef_f * f.x, A.ep.coef_f * f.y, A.ep.coef_f * f.z, A.ep.coef_f * f.w);
-      if (nt > 0) GRAND_FMA4(y, A.ep.coef[0], E.t0[r]);
-      if (nt > 1) GRAND_FMA4(y, A.ep.coef[1], E.t1[r]);
-      if (nt > 2) GRAND_FMA4(y, A.ep.coef[2], E.t2[r]);
-      if (nt > 3) GRAND_FMA4(y, A.ep.coef[3], E.t3[r]);
+      const float cf = epi_coef_f(A.ep);
+      float4 y = make_float4(cf * f.x, cf * f.y, cf * f.z, cf * f.w);
+      if (nt > 0) GRAND_FMA4(y, epi_coef(A.ep, 0), E.t0[r]);
+      if (nt > 1) GRAND_FMA4(y, epi_coef(A.ep, 1), E.t1[r]);
+      if (nt > 2) GRAND_FMA4(y, epi_coef(A.ep, 2), E.t2[r]);
+      if (nt > 3) GRAND_FMA4(y, epi_coef(A.ep, 3), E.t3[r]);
       for (int t = 4; t < nt; ++t) {                               // dopri5 stages have up to 7 terms
-        const float ct = A.ep.coef[t];
+        const float ct = epi_coef(A.ep, t);
         const float4 v = ld_stream4_hint(A.ep.term[t] + o, pol_stream);
         GRAND_FMA4(y, ct, v);
       }

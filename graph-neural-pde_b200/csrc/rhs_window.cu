@@ -220,18 +220,19 @@ __device__ __forceinline__ void finish_row(const RhsArgs& A, int row, int lane, 
       }
       if (A.ep.f_out != nullptr) st_stream4_hint(A.ep.f_out + base + c, f, pol_stream);
       if (A.ep.y_out != nullptr) {
-        float4 y = make_float4(A.ep.coef_f * f.x, A.ep.coef_f * f.y, A.ep.coef_f * f.z, A.ep.coef_f * f.w);
+        const float cf = epi_coef_f(A.ep);
+        float4 y = make_float4(cf * f.x, cf * f.y, cf * f.z, cf * f.w);
 #pragma unroll
         for (int t = 0; t < kTB; ++t) {
           if (t < A.ep.n_terms) {
-            const float ct = A.ep.coef[t];
+            const float ct = epi_coef(A.ep, t);
             y.x = fmaf(ct, tv[t].x, y.x); y.y = fmaf(ct, tv[t].y, y.y);
             y.z = fmaf(ct, tv[t].z, y.z); y.w = fmaf(ct, tv[t].w, y.w);
           }
         }
 #if GRAND_EPI_TERMS_BATCH == 4
         for (int t = kTB; t < A.ep.n_terms; ++t) {
-          const float ct = A.ep.coef[t];
+          const float ct = epi_coef(A.ep, t);
           const float4 v = ld_stream4_hint(A.ep.term[t] + base + c, pol_stream);
           y.x = fmaf(ct, v.x, y.x); y.y = fmaf(ct, v.y, y.y); y.z = fmaf(ct, v.z, y.z); y.w = fmaf(ct, v.w, y.w);
         }
@@ -246,7 +247,7 @@ __device__ __forceinline__ void finish_row(const RhsArgs& A, int row, int lane, 
 #pragma unroll
           for (int u = 0; u < kTB; ++u) {
             if (t0 + u < A.ep.n_terms) {
-              const float ct = A.ep.coef[t0 + u];
+              const float ct = epi_coef(A.ep, t0 + u);
               y.x = fmaf(ct, tw[u].x, y.x); y.y = fmaf(ct, tw[u].y, y.y);
               y.z = fmaf(ct, tw[u].z, y.z); y.w = fmaf(ct, tw[u].w, y.w);
             }
@@ -262,10 +263,10 @@ __device__ __forceinline__ void finish_row(const RhsArgs& A, int row, int lane, 
       if (A.ep.x0 != nullptr) f += beta * __ldg(A.ep.x0 + base + c);
       if (A.ep.f_out != nullptr) A.ep.f_out[base + c] = f;
       if (A.ep.y_out != nullptr) {
-        float y = A.ep.coef_f * f;
+        float y = epi_coef_f(A.ep) * f;
 #pragma unroll
         for (int t = 0; t < GRAND_MAX_TERMS; ++t)
-          if (t < A.ep.n_terms) y = fmaf(A.ep.coef[t], __ldg(A.ep.term[t] + base + c), y);
+          if (t < A.ep.n_terms) y = fmaf(epi_coef(A.ep, t), __ldg(A.ep.term[t] + base + c), y);
         A.ep.y_out[base + c] = y;
       }
     }

@@ -143,8 +143,9 @@ class Dopri5:
     self.t0 = self.t1 = float(t0)
     self.have_interp = False
 
-  def adaptive_step(self):
-    """One attempted step; returns True when accepted.  On accept the state (ycur, k[0]) moves to t1."""
+  def adaptive_step(self, force_accept=None):
+    """One attempted step; returns True when accepted.  On accept the state (ycur, k[0]) moves to t1.  `force_accept`
+    overrides the controller's decision (replay of another implementation's step sequence in the parity tests)."""
     p, k, func = self.prob, self.k, self.func
     t0, dt = self.t1, self.dt
     assert t0 + dt > t0, 'underflow in dt {}'.format(dt)
@@ -163,7 +164,8 @@ class Dopri5:
     y1 = inp   # the 6th stage input is the 5th-order solution (c_sol == last beta row, FSAL)
     err_terms = [(k[j], _f32(h * _f32(DP_C_ERROR[j]))) for j in range(7) if DP_C_ERROR[j] != 0]
     ratio = self._rms(err_terms, self.ycur, y1, self.atol, self.rtol)
-    accept = ratio <= 1
+    accept = ratio <= 1 if force_accept is None else bool(force_accept)
+    self.last_ratio = ratio
     self.attempts += 1
     if accept:
       self.accepted += 1
@@ -216,6 +218,74 @@ class Dopri5:
     return out
 
 
+class Dopri5Device:
+  """dopri5 with the controller on the device (grand_dopri5_create / launch, csrc/dopri5_device.cu): one CUDA Graph
+  with a conditional WHILE node per (function, shape, tolerances, time span); the host launches it and reads the
+  24-byte counters once per integration (NFE accounting).  Cached on the engine."""
+
+  def __init__(self, func, y0, t0, t1, rtol, atol, max_attempts):
+    import ctypes as C
+    self.prob = NativeProblem(func, y0)
+    eng = self.prob.engine
+    n = self.prob.n
+    self.planes = eng.buffer('dopri_dev', rows=13 * n)
+    self.y0 = eng.buffer('dopri_dev_y0', rows=n)
+    self.out = eng.buffer('dopri_dev_out', rows=n)
+    self.state = torch.zeros(C.sizeof(N.GrandDopri5State), dtype=torch.uint8, device=y0.device)
+    self.ep = self.prob.epilogue()
+    plan = C.c_void_p()
+    ws = eng.workspace(self.prob.spec)
+    N.check(N.lib().grand_dopri5_create(
+      C.byref(eng.plan.struct()), C.byref(self.prob.spec.struct) if self.prob.spec is not None else None,
+      N.ptr(self.prob.w_csr), eng.d, C.byref(ws), C.byref(self.ep), self.y0.data_ptr(), self.out.data_ptr(),
+      self.planes.data_ptr(), self.state.data_ptr(), float(t0), float(t1), float(rtol), float(atol), int(max_attempts),
+      C.byref(plan)))
+    self.plan = plan
+    self.key = None
+
+  def __del__(self):
+    try:
+      if getattr(self, 'plan', None):
+        N.lib().grand_dopri5_destroy(self.plan)
+    except Exception:
+      pass
+
+  def run(self, y0):
+    self.y0.copy_(y0)
+    N.check(N.lib().grand_dopri5_launch(self.plan, N.current_stream(y0.device)))
+    return self.out
+
+  def counters(self):
+    st = N.GrandDopri5State.from_buffer_copy(self.state.cpu().numpy().tobytes())
+    return st
+
+
+def integrate_dopri5_device(func, y0, t, rtol, atol):
+  """y(t[0]) -> y(t[1]) with the device-side controller; returns (out [2, N, d], counters)."""
+  prob_engine = func.engine(y0)
+  t0, t1 = float(t[0]), float(t[-1])
+  budget = int(func.opt.get('max_nfe', 1000)) - int(func.nfe) - 2
+  max_attempts = max(1, budget // 6 + 1)
+  ptrs = tuple(p.data_ptr() for p in func.parameters())
+  key = ('dopri5_dev', tuple(y0.shape), t0, t1, float(rtol), float(atol), max_attempts, ptrs, id(prob_engine.plan),
+         None if getattr(func, 'x0', None) is None else func.x0.data_ptr())
+  cache = prob_engine._state.setdefault('_dopri5_dev', {})
+  solver = cache.get(key)
+  if solver is None:
+    cache.clear()                     # one plan per engine: buffers are shared
+    solver = Dopri5Device(func, y0, t0, t1, rtol, atol, max_attempts)
+    cache[key] = solver
+  z = solver.run(y0)
+  st = solver.counters()              # the one device -> host read of the integration
+  if st.status != 0:
+    raise AssertionError('underflow in dt {}'.format(st.dt))
+  func._bump_nfe(int(st.nfe))
+  out = torch.empty((2,) + tuple(y0.shape), dtype=y0.dtype, device=y0.device)
+  out[0] = y0
+  out[1] = z
+  return out, st
+
+
 def integrate_dopri5(func, y0, t, rtol, atol, on_step=None, max_steps=None):
   solver = Dopri5(func, y0, rtol, atol)
   tt = [float(v) for v in t]
@@ -257,6 +327,10 @@ def _check_call(y0, method, options, event_fn):
 def _native_solution(func, y0, t, method, options, rtol, atol):
   if method in FIXED_METHODS:
     return integrate_fixed(func, y0, t, method, options['step_size'])
+  import os
+  if len(t) == 2 and float(t[-1]) > float(t[0]) and os.environ.get('GRAND_DOPRI5', 'device') == 'device':
+    out, _ = integrate_dopri5_device(func, y0, t, rtol, atol)     # controller on the device: one graph launch
+    return out
   out, _ = integrate_dopri5(func, y0, t, rtol, atol)
   return out
 

@@ -101,6 +101,26 @@ def reference_best_params(cmd_opt):
   return opt
 
 
+def training_blockers(opt):
+  """Reasons why `opt` cannot be TRAINED on this engine (forward / evaluation of every one of them runs): checked before
+  the first epoch so that an unsupported configuration fails at start-up with one message, not mid-epoch."""
+  why = []
+  if opt['block'] == 'attention':
+    why.append("block='attention': gradients through the attention frozen at x(0) (reference "
+               "src/block_transformer_attention.py:36-39) are not built")
+  if opt['function'] == 'GAT':
+    why.append("function='GAT': the GAT scorer is forward-only")
+  if opt['function'] == 'transformer' and (opt['attention_type'] != 'scaled_dot' or opt['square_plus']
+                                          or opt['attention_norm_idx'] != 0):
+    why.append('transformer backward is built for attention_type=scaled_dot, softmax, attention_norm_idx=0')
+  if opt['function'] == 'transformer' and opt['hidden_dim'] % 4 != 0:
+    why.append('transformer backward needs hidden_dim %% 4 == 0 (got %d)' % opt['hidden_dim'])
+  if opt.get('adjoint') and opt.get('adjoint_method') not in ('euler', 'midpoint', 'rk4'):
+    why.append('adjoint_method=%r: only the fixed-grid adjoint solvers (euler, midpoint, rk4) are built'
+               % opt.get('adjoint_method'))
+  return why
+
+
 def main(cmd_opt):
   opt = dict(cmd_opt)
   if opt.get('best_params') == 'reference':
@@ -117,6 +137,10 @@ def main(cmd_opt):
       raise NotImplementedError('--%s is outside the grand_b200 hot-path scope (SURVEY.md section 8)' % flag)
   if opt['method'] is None:
     opt['method'] = 'dopri5'   # the reference passes None through to torchdiffeq, whose default is dopri5
+  blockers = training_blockers(opt) if opt['epoch'] > 1 else []
+  if blockers:
+    raise NotImplementedError('this configuration cannot be trained on the grand_b200 engine yet (its forward and '
+                              'evaluation run): ' + '; '.join(blockers))
   if not torch.cuda.is_available():
     raise RuntimeError('run_GNN.py of grand_b200 needs a CUDA device (sm_100a); there is no CPU fallback')
   device = torch.device('cuda')

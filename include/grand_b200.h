@@ -156,6 +156,8 @@ typedef struct grand_epilogue {
   const grand_peers* peers;    /* or null.  Non-null: y_out lies in the arena and every finished row of it is ALSO
                                   stored into the halo of the peers that reference it, from the same kernel, as the
                                   row is produced (the exchange overlaps the rest of the launch)         */
+  const float* coef_dev;       /* or null.  Non-null: device [1 + GRAND_MAX_TERMS] = coef_f, coef[0..] read BY THE KERNEL
+                                  instead of the host values above (device-side step-size control, grand_dopri5_*) */
 } grand_epilogue;
 
 /* caller-owned scratch; sizes from grand_workspace_sizes */
@@ -250,6 +252,32 @@ int grand_lincomb(int64_t n, int32_t n_terms, const float* const* term, const fl
  * *sumsq (caller zeroes it), err = sum_t coef[t] * k[t]   (torchdiffeq _compute_error_ratio with rms norm). */
 int grand_error_sumsq(int64_t n, int32_t n_terms, const float* const* k, const float* coef, const float* y0,
                       const float* y1, float atol, float rtol, double* sumsq, void* stream);
+
+/*
+ * dopri5 with the controller ON THE DEVICE (torchdiffeq RKAdaptiveStepsizeODESolver semantics, witness reference
+ * src/early_stop_solver.py:30-86): initial step selection, the attempt loop, accept / reject, the step-size update and
+ * the final dense-output evaluation at t1 are ONE CUDA Graph whose attempt loop is a conditional WHILE node; the host
+ * launches it and reads nothing back until it wants the counters.  Integrates y(t0) -> y(t1) for the two-point time
+ * vector the reference's blocks use.  All buffers caller-owned: `planes` = 13 x [n_rows, d] floats (ycur, ya, yb, ymid,
+ * yprev, fprev, k0..k6), `state` = device memory of sizeof(grand_dopri5_state); y0 is read, `out` receives y(t1).
+ * a == null selects the Laplacian function with w_csr.  create / destroy are the only calls that allocate (the graph).
+ */
+#define GRAND_DOPRI5_COEFS 72
+typedef struct grand_dopri5_state {
+  double t, t_prev, dt, t_end;   /* time of ycur, start of the last accepted step, next step size, target        */
+  double acc[3];                 /* sum-of-squares accumulators of the norm kernels                              */
+  double h0;                     /* probe size of the initial step selection                                     */
+  float rtol, atol;
+  int32_t numel, attempts, accepted, nfe, max_attempts, accept, have_interp, status;  /* status != 0: dt underflow */
+  float coef[GRAND_DOPRI5_COEFS];/* every dt-dependent coefficient of the current attempt (stage combines, error, dense output) */
+} grand_dopri5_state;
+typedef struct grand_dopri5_plan grand_dopri5_plan;
+int grand_dopri5_create(const grand_graph* g, const grand_attention* a, const float* w_csr, int32_t d,
+                        const grand_workspace* ws, const grand_epilogue* residual, const float* y0, float* out,
+                        float* planes, grand_dopri5_state* state, double t0, double t1, float rtol, float atol,
+                        int32_t max_attempts, grand_dopri5_plan** plan);
+int grand_dopri5_launch(grand_dopri5_plan* plan, void* stream);
+int grand_dopri5_destroy(grand_dopri5_plan* plan);
 
 /* ---- node-partitioned multi-GPU over peer-mapped memory (see grand_peers) ------------------------------------------
  * Arena life cycle (the only entry points of this library that allocate): cudaMalloc / cudaIpcGetMemHandle /

@@ -155,6 +155,80 @@ def test_model_early_golden(golden):
       assert abs(model.odeblock.odefunc.nfe - out['nfe']) <= 18, name
 
 
+def _oracle_func_of(c):
+  holder = {}
+  real = O.block_forward
+
+  def capture(func, xx, T, o, _real=real):
+    holder['f'] = func
+    return _real(func, xx, T, {**o, 'method': 'euler', 'step_size': o['time']})
+
+  O.block_forward = capture
+  try:
+    C.oracle_block(c)
+  finally:
+    O.block_forward = real
+  return holder['f']
+
+
+def test_dopri5_replay_of_oracle_steps(golden):
+  """Implementation-independent end-state parity for the adaptive solver: the oracle's sequence of attempted steps
+  (t, dt, accept) is replayed on the GPU solver -- same steps, same accept decisions, same dense-output evaluation --
+  and the end state must agree to 1e-5 (the free-running controllers may legitimately pick step sizes a few % apart,
+  see test_blocks_golden)."""
+  from graph_neural_pde_b200.odeint import Dopri5
+  for name in ['block/transformer_constant/dopri5_h1.0/v0', 'block/laplacian_constant/dopri5_h1.0/v2']:
+    c = golden[name]
+    block, opt = _build_block(c)
+    x = c['inputs']['x'].to(DEV)
+    block.set_x0(x)
+    atol, rtol = O.block_tolerances(opt)
+    f = _oracle_func_of(c)
+    xc = c['inputs']['x']
+    stats = O.Dopri5Stats()
+    T = float(opt['time'])
+    want = O.odeint_dopri5(f, xc, torch.tensor([0.0, T]), rtol, atol, stats=stats)[1]
+    assert stats.accepted >= 1
+    with torch.no_grad():
+      solver = Dopri5(block.odefunc, x, rtol, atol)
+      solver.before_integrate(0.0)
+      for (t0s, dts, ratio, accept) in stats.step_sizes:
+        assert abs(solver.t1 - t0s) <= 1e-12 * max(1.0, abs(t0s))
+        solver.dt = dts
+        solver.adaptive_step(force_accept=accept)
+        assert abs(solver.last_ratio - ratio) <= 2e-2 * max(ratio, 1e-3), '%s ratio %g vs %g' % (name, solver.last_ratio, ratio)
+      out = torch.empty_like(x)
+      solver.interpolate(T, out)
+    C.assert_close(out, want, C.RTOL, name + ' end state under the replayed step sequence')
+
+
+def test_dopri5_device_controller_matches_host_controller(golden, monkeypatch):
+  """grand_dopri5_* (controller on the device, one CUDA Graph with a WHILE node) against the host-driven solver: the
+  same attempts, accepted steps, NFE and end state (both do the same fp32 stage arithmetic; the controllers' float64
+  scalar math may differ in the last bit of pow())."""
+  from graph_neural_pde_b200 import odeint as OD
+  for name in ['block/transformer_constant/dopri5_h1.0/v0', 'block/laplacian_constant/dopri5_h1.0/v2']:
+    c = golden[name]
+    block, opt = _build_block(c)
+    x = c['inputs']['x'].to(DEV)
+    block.set_x0(x)
+    atol, rtol = O.block_tolerances(opt)
+    t = torch.tensor([0.0, float(opt['time'])])
+    with torch.no_grad():
+      block.odefunc.nfe = 0
+      out_h, solver = OD.integrate_dopri5(block.odefunc, x, t, rtol, atol)
+      nfe_h = block.odefunc.nfe
+      block.odefunc.nfe = 0
+      out_d, st = OD.integrate_dopri5_device(block.odefunc, x, t, rtol, atol)
+      nfe_d = block.odefunc.nfe
+      out_d2, st2 = OD.integrate_dopri5_device(block.odefunc, x, t, rtol, atol)      # relaunch of the cached graph
+    assert (st.attempts, st.accepted) == (solver.attempts, solver.accepted), \
+        '%s attempts/accepted device %d/%d host %d/%d' % (name, st.attempts, st.accepted, solver.attempts, solver.accepted)
+    assert nfe_d == nfe_h == 2 + 6 * solver.attempts
+    C.assert_close(out_d[1], out_h[1], 2e-6, name + ' device vs host controller')
+    assert torch.equal(out_d2[1], out_d[1]) and st2.attempts == st.attempts
+
+
 def test_dopri5_single_attempt_vs_oracle(golden):
   """One attempted Dormand-Prince step from identical (y, f0, dt): stage values, 5th-order solution and the error
   ratio against the oracle's _dopri5_rk_step -- pins the step arithmetic itself to 1e-5."""

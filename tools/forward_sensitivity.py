@@ -11,7 +11,9 @@ import torch
 ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), '..'))
 sys.path.insert(0, ROOT)
 import bench  # noqa: E402
-from graph_neural_pde_b200 import _native as N  # noqa: E402  (bench loaded the package)
+from __graft_entry__ import load_package  # noqa: E402
+load_package()
+from graph_neural_pde_b200 import _native as N  # noqa: E402
 from oracle import grand_oracle as O  # noqa: E402
 
 dev = torch.device('cuda:0')
