@@ -33,6 +33,16 @@ def _transposed_engine(func, x):
   return cached[1]
 
 
+def _same_engine(ctx, func, x):
+  """The engine (graph plan) captured at forward time; a graph that was re-assigned between forward and backward
+  (hard-attention re-selection, an outside `edge_index` assignment) is an error, as a version-counter mismatch is for
+  tensors in plain autograd."""
+  eng = func.engine(x)
+  if eng is not ctx.engine:
+    raise RuntimeError('grand_b200 backward: the graph of this ODE function changed between forward and backward')
+  return eng
+
+
 def _sigmoid_grad(alpha_train, no_alpha_sigmoid):
   if no_alpha_sigmoid:
     return torch.ones_like(alpha_train)
@@ -64,10 +74,14 @@ class TransformerRhsFn(torch.autograd.Function):
     if not spec.fused:
       raise NotImplementedError('grand_b200 backward is built for attention_type=scaled_dot, softmax, '
                                 'attention_norm_idx=0 (the other configurations run forward-only)')
+    if x.shape[1] % 4 != 0:
+      raise NotImplementedError('grand_b200 backward needs a state width that is a multiple of 4 (got %d)' % x.shape[1])
     f = torch.empty_like(x)
     ep = func.residual_epilogue(eng, func.stage_x0(eng), f_out=f)
     eng.rhs_attention(spec, x, ep)
     ctx.func = func
+    ctx.engine = eng                      # the graph plan and source term this evaluation was computed with
+    ctx.x0 = func.x0 if func.opt['add_source'] else None
     ctx.save_for_backward(x, wq, bq, wk, bk, alpha_train, beta_train)
     return f
 
@@ -77,7 +91,7 @@ class TransformerRhsFn(torch.autograd.Function):
     func = ctx.func
     opt = func.opt
     g = g.contiguous()
-    eng = func.engine(x)
+    eng = _same_engine(ctx, func, x)
     spec = func.multihead_att_layer.spec(eng)
     no_sig = bool(opt['no_alpha_sigmoid'])
     # 1. edge phase
@@ -99,7 +113,7 @@ class TransformerRhsFn(torch.autograd.Function):
       eng.rhs_attention(spec, x, ep_r)
       dalpha = (g * r).sum() * _sigmoid_grad(alpha_train.detach(), no_sig)
     if ctx.needs_input_grad[6] and opt['add_source']:
-      dbeta = (g * func.x0).sum()
+      dbeta = (g * ctx.x0).sum()
     return gx, dwq, dbq, dwk, dbk, dalpha, dbeta, None
 
 
@@ -114,6 +128,9 @@ class LaplacianRhsFn(torch.autograd.Function):
     ep = func.residual_epilogue(eng, func.stage_x0(eng), f_out=f)
     eng.rhs_laplacian(func.weights_csr(eng), x, ep)
     ctx.func = func
+    ctx.engine = eng
+    ctx.x0 = func.x0 if func.opt['add_source'] else None
+    ctx.edge_values = func.edge_values().detach()
     ctx.save_for_backward(x, alpha_train, beta_train)
     return f
 
@@ -124,19 +141,19 @@ class LaplacianRhsFn(torch.autograd.Function):
     opt = func.opt
     g = g.contiguous()
     no_sig = bool(opt['no_alpha_sigmoid'])
-    eng = func.engine(x)
+    eng = _same_engine(ctx, func, x)
     eng_t = _transposed_engine(func, x)
     gx = torch.empty_like(x)
     ep_t = RhsEngine.epilogue(alpha_train.detach(), None, None, no_sig, f_out=gx)
-    eng_t.rhs_laplacian(eng_t.edge_values_to_csr(func.edge_values().detach()), g, ep_t)
+    eng_t.rhs_laplacian(eng_t.edge_values_to_csr(ctx.edge_values), g, ep_t)
     dalpha = dbeta = None
     if ctx.needs_input_grad[1]:
       r = torch.empty_like(x)
       ep_r = RhsEngine.epilogue(_ConstOne.get(x.device), None, None, True, f_out=r)
-      eng.rhs_laplacian(func.weights_csr(eng), x, ep_r)
+      eng.rhs_laplacian(eng.edge_values_to_csr(ctx.edge_values), x, ep_r)
       dalpha = (g * r).sum() * _sigmoid_grad(alpha_train.detach(), no_sig)
     if ctx.needs_input_grad[2] and opt['add_source']:
-      dbeta = (g * func.x0).sum()
+      dbeta = (g * ctx.x0).sum()
     return gx, dalpha, dbeta, None
 
 

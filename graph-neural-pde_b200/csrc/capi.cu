@@ -8,9 +8,9 @@
 namespace grand {
 
 static thread_local char g_error[512] = "";
-static int64_t g_launches = 0;
+static int64_t g_launches = 0;   // diagnostic counter only (grand_launch_count); updated atomically
 
-void count_launch(int n) { g_launches += n; }
+void count_launch(int n) { __atomic_fetch_add(&g_launches, (int64_t)n, __ATOMIC_RELAXED); }
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -181,7 +181,7 @@ extern "C" {
 
 int grand_abi_version(void) { return GRAND_ABI_VERSION; }
 
-int64_t grand_launch_count(void) { return g_launches; }
+int64_t grand_launch_count(void) { return __atomic_load_n(&g_launches, __ATOMIC_RELAXED); }
 
 const char* grand_last_error(void) { return g_error; }
 

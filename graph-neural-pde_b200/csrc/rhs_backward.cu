@@ -176,11 +176,8 @@ int rhs_attention_backward_impl(const grand_graph* g, const grand_attention* a, 
   const size_t smem = (size_t)kBwdWarps * ((size_t)(GRAND_TILE + kBwdMaxRows) * a->d * sizeof(float) + 16);
   GRAND_REQUIRE(smem <= 227 * 1024, GRAND_EUNSUPPORTED, "rhs_attention_backward: state width %d needs %zu B of shared "
                 "memory per block", a->d, smem);
-  static size_t configured = 48 * 1024;
-  if (smem > configured) {
+  if (smem > 48 * 1024)   // per device and cheap: set on every launch that needs it (no process-wide "already done" flag)
     GRAND_CUDA_OK(cudaFuncSetAttribute(rhs_attention_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
-  }
   if (g->n_split_tiles > 0) {
     GRAND_REQUIRE(row_dot != nullptr && ws->row_stats != nullptr, GRAND_EINVAL,
                   "rhs_attention_backward: graph has long rows, row_dot / row_stats are null");

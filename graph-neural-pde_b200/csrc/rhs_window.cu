@@ -746,11 +746,8 @@ static int launch_rhs_inst(const RhsArgs& A, cudaStream_t stream) {
   if (STAGE == STAGE_CPASYNC || STAGE == STAGE_BULK) smem = (size_t)kRhsWarps * ((size_t)GRAND_TILE * A.d * sizeof(float) + 16);
   if (STAGE == STAGE_ROWBUF) smem = (size_t)kRhsWarps * GRAND_MAX_PACKED_ROWS * A.d * sizeof(float);
   auto kern = rhs_window_kernel<MODE, VEC, R, STAGE>;
-  static size_t configured = 48 * 1024;
-  if (smem > configured) {
+  if (smem > 48 * 1024)   // per device and cheap: set on every launch that needs it
     GRAND_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
-  }
   kern<<<grid, kRhsThreads, smem, stream>>>(A);
   GRAND_CUDA_OK(cudaGetLastError());
   count_launch();

@@ -242,6 +242,8 @@ class RhsEngine:
     if entry is None:
       # first call: run eagerly (also the warm-up cudaFuncSetAttribute etc. need), capture on the next one
       launch()
+      while len(self._graphs) >= 8:       # keys hold device addresses of temporaries: bound the cache, oldest out
+        self._graphs.pop(next(iter(self._graphs)))
       self._graphs[key] = 'warm'
       return y
     if entry == 'warm':

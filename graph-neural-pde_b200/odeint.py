@@ -299,8 +299,9 @@ def integrate_dopri5(func, y0, t, rtol, atol, on_step=None, max_steps=None):
       n_steps += 1
       if on_step is not None:
         on_step(solver, accepted)
-    if max_steps is not None and n_steps >= max_steps and tt[i] > solver.t1:
-      # EarlyStopDopri5.advance: out of test steps -> return the state at the last accepted t1
+    if max_steps is not None and n_steps >= max_steps:
+      # EarlyStopDopri5.advance (reference src/early_stop_solver.py:76-86): `if n_steps < max_test_steps: interpolate else:
+      # the state at t1` -- also when the last allowed step happened to reach the target time
       out[i] = solver.ycur
     elif not solver.have_interp:
       out[i] = solver.ycur
