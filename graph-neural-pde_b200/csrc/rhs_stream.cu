@@ -54,6 +54,12 @@ __device__ __forceinline__ float stream_score(const AttnView& a, const float* __
 // a_eh = exp(s - max) / (sum + 1e-16)  (PyG softmax, reference :213).  The quotient is taken with the hardware reciprocal
 // (2 ulp, measured 2e-7 of the output against the IEEE division and 11 us per launch faster on ogbn-arxiv); the
 // exponential stays expf unless GRAND_STREAM_FAST_EXP asks for ex2.approx (absolute error <= 3e-7 of the row maximum).
+// a 64-byte K / Q row (16 floats) as four float4: two 256-bit loads (sm_100a LDG.E.256) -- half the load instructions
+// and, for a lane-per-edge gather that touches 32 different lines, half the L1 wavefronts of four 128-bit loads
+__device__ __forceinline__ void load_row16(const float* p, float4 (&v)[4]) {
+  const float8 a = ldg8(p), b = ldg8(p + 8);
+  v[0] = a.lo; v[1] = a.hi; v[2] = b.lo; v[3] = b.hi;
+}
 __device__ __forceinline__ float attn_div(float e, float l) {
 #if GRAND_STREAM_FAST_DIV
   return __fdividef(e, l + 1e-16f);
@@ -310,11 +316,8 @@ __device__ __forceinline__ float window_weight(const RhsArgs& A, int lane, int i
     if (A.a.dk == 4 && vec4 && H == 4) {
       // d_k = 4, 4 heads (ogbn-arxiv: ad 16): a head is ONE float4 of the Q / K row; all 8 loads first
       float4 qv[4], kv[4];
-#pragma unroll
-      for (int h = 0; h < 4; ++h) {
-        qv[h] = ldg4(qi + 4 * h);            // idle lanes read row0's Q row and K row 0: harmless, no predicates
-        kv[h] = ldg4(kj + 4 * h);
-      }
+      load_row16(qi, qv);                    // idle lanes read row0's Q row and K row 0: harmless, no predicates
+      load_row16(kj, kv);
       float s[4], m[4], ex[4], l[4];
 #pragma unroll
       for (int h = 0; h < 4; ++h) {
@@ -422,8 +425,7 @@ __device__ __forceinline__ void process_segment(const RhsArgs& A, const int4 des
         const float ew = A.a.edge_weight_csr != nullptr ? __ldg(A.a.edge_weight_csr + p) : 1.f;
         if (dk4) {
           float4 kv[4];
-#pragma unroll
-          for (int h = 0; h < 4; ++h) kv[h] = ldg4(kj + 4 * h);
+          load_row16(kj, kv);
 #pragma unroll
           for (int h = 0; h < 4; ++h) {
             const float4 qh = ldg4(qi + 4 * h);                     // same address in every lane: one broadcast line
@@ -489,8 +491,7 @@ __device__ __forceinline__ void process_segment(const RhsArgs& A, const int4 des
       const float ew = (valid && A.a.edge_weight_csr != nullptr) ? __ldg(A.a.edge_weight_csr + p) : 1.f;
       if (dk4) {
         float4 kv[4];
-#pragma unroll
-        for (int h = 0; h < 4; ++h) kv[h] = ldg4(kj + 4 * h);       // idle lanes read K row 0: harmless
+        load_row16(kj, kv);                                         // idle lanes read K row 0: harmless
 #pragma unroll
         for (int h = 0; h < 4; ++h) {
           const float4 qh = ldg4(qi + 4 * h);
