@@ -381,7 +381,8 @@ def measure_workload(name, args, dev, full):
   torch.cuda.synchronize()
   warm_s = warm_up(step_resident, min_s=1.0 if full else 0.3, max_s=5.0 if full else 1.5)
 
-  res = {'name': name, 'evals': evals, 'launches_per_step': launches_per_step, 'n': n, 'e': e, 'd': d, 'ad': ad,
+  res = {'name': name, 'data_source': getattr(ds, 'source', 'synthetic'),
+         'evals': evals, 'launches_per_step': launches_per_step, 'n': n, 'e': e, 'd': d, 'ad': ad,
          'heads': heads, 'opt': opt, 'warm_up_seconds': warm_s}
   with ClockSampler(dev.index or 0) as clocks:
     # ---- timed region 1: inputs resident in HBM ----
@@ -547,6 +548,66 @@ def sub_result(res, peak):
           'cpu_baseline': res['cpu'], 'clocks': res['clocks']}
 
 
+def run_native_train(args):
+  """--mode train: one training step of the block = forward + backward.  ogbn-arxiv: the reference's
+  ray_tune configuration (src/ray_tune.py:19-22): adjoint rk4, adjoint_step_size 1 -> forward 24 RHS evaluations on the
+  fused engine, backward 24 stages of the augmented system, each = one forward RHS + its vector-Jacobian product."""
+  from __graft_entry__ import load_package
+  load_package()
+  from graph_neural_pde_b200 import _native as N
+  dev = torch.device('cuda:0')
+  torch.cuda.set_device(dev)
+  name = args.workload
+  ds, opt, x_host = build_workload(name)
+  if opt['method'] != 'rk4' or opt['function'] != 'transformer':
+    raise SystemExit('--mode train is wired for the rk4 attention workloads (ogbn-arxiv, Cora, Cora-BLEND)')
+  from graph_neural_pde_b200.block_constant import ConstantODEblock
+  from graph_neural_pde_b200.function_transformer_attention import ODEFuncTransformerAtt
+  from graph_neural_pde_b200.synthetic import Data
+  opt = dict(opt, adjoint=True, adjoint_method='rk4', adjoint_step_size=opt['step_size'])
+  n, d = x_host.shape
+  data = Data(x=x_host, edge_index=ds.data.edge_index, edge_attr=None, num_nodes=n)
+  block = ConstantODEblock(ODEFuncTransformerAtt, (), opt, data, dev, t=torch.tensor([0, opt['time']])).to(dev)
+  init_trained_like(block)
+  block.train()
+  func = block.odefunc
+  e = int(func.edge_index.shape[1])
+  x_dev = x_host.to(dev)
+  w = torch.randn(n, d, generator=torch.Generator().manual_seed(1)).to(dev) / n
+
+  def step():
+    func.nfe = 0
+    for p in block.parameters():
+      p.grad = None
+    xin = x_dev.clone().requires_grad_(True)
+    block.set_x0(xin.detach())
+    z = block(xin)
+    (z * w).sum().backward()
+    return xin.grad
+
+  before = N.lib().grand_launch_count()
+  step()
+  launches = int(N.lib().grand_launch_count() - before)
+  torch.cuda.synchronize()
+  warm_up(step, min_s=1.0, max_s=5.0)
+  steps = max(2, min(args.steps, 5))
+  with ClockSampler(0) as clocks:
+    rep = timed_repeats(step, steps, args.repeats)
+  ms = median(rep)
+  fwd = 4 * len(__import__('graph_neural_pde_b200.engine', fromlist=['fixed_grid_dts']).fixed_grid_dts(0.0, opt['time'], opt['step_size'])[0])
+  line = {'metric': METRIC, 'mode': 'train (forward + adjoint backward)', 'value': e * opt['heads'] * 2 * fwd / (ms * 1e-3),
+          'unit': UNIT, 'n_gpus': 1, 'steps': steps, 'warmup': args.warmup, 'ms_per_step': ms, 'higher_is_better': True,
+          'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+          'config': workload_config(name, opt, n, e),
+          'timing': {'ms_per_step_repeats': rep, 'repeats': args.repeats, 'statistic': 'median'},
+          'rhs_evals_forward': fwd, 'adjoint_stages_backward': fwd,
+          'value_note': 'edges*heads * (forward RHS evaluations + backward adjoint stages) / time; a backward stage is one '
+                        'RHS evaluation plus its vector-Jacobian product (edge-phase VJP kernel, transposed aggregation, '
+                        'cuBLAS tails)',
+          'gpu_launches_per_step': launches, 'clocks': clocks.summary()}
+  emit(line)
+
+
 def run_native_single(args):
   from __graft_entry__ import load_package
   load_package()
@@ -571,7 +632,8 @@ def run_native_single(args):
   line = {
     'metric': METRIC, 'value': e * heads * evals / (ms_step * 1e-3), 'unit': UNIT, 'n_gpus': 1, 'steps': args.steps,
     'warmup': args.warmup, 'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None,
-    'dtype': 'f32', 'data': 'synthetic',
+    'dtype': 'f32',
+    'data': 'synthetic' if res['data_source'] == 'synthetic' else 'real edge list from %s, synthetic state' % res['data_source'],
     'config': workload_config(name, opt, n, e),
     'timing': {'ms_per_step_repeats': res['ms_repeats'], 'repeats': args.repeats, 'statistic': 'median',
                'warm_up_seconds': res['warm_up_seconds'],
@@ -810,6 +872,7 @@ def main():
   ap.add_argument('--impl', default='native', choices=['native', 'reference'])
   ap.add_argument('--skip-cpu', action='store_true', help='skip the CPU baseline leg (kernel A/B runs)')
   ap.add_argument('--workload', default='ogbn-arxiv', choices=sorted(WORKLOADS))
+  ap.add_argument('--mode', default='forward', choices=['forward', 'train'], help='train: forward + adjoint backward of the block')
   ap.add_argument('--transport', default=None, choices=['peer', 'nccl'], help='multi-GPU halo transport (default peer)')
   ap.add_argument('--repeats', type=int, default=5, help='timed repeats of --steps steps each; the median is reported')
   ap.add_argument('--no-others', action='store_true', help='skip the other BASELINE configurations (kernel A/B runs)')
@@ -820,6 +883,8 @@ def main():
     return run_reference(args, rank, world)
   if world > 1 or args.gpus > 1:
     return run_native_multi(args, rank, world)
+  if args.mode == 'train':
+    return run_native_train(args)
   return run_native_single(args)
 
 

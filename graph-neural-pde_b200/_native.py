@@ -73,7 +73,8 @@ class GrandDopri5State(C.Structure):
 class GrandWorkspace(C.Structure):
   _fields_ = [('q', C.c_void_p), ('k', C.c_void_p), ('scores', C.c_void_p), ('seg_stats', C.c_void_p),
               ('split_stats', C.c_void_p), ('row_stats', C.c_void_p), ('split_partial', C.c_void_p), ('split_counter', C.c_void_p),
-              ('gmax', C.c_void_p), ('lrow_stats', C.c_void_p), ('lpartial', C.c_void_p), ('lcounter', C.c_void_p)]
+              ('gmax', C.c_void_p), ('lrow_stats', C.c_void_p), ('lpartial', C.c_void_p), ('lcounter', C.c_void_p),
+              ('coop_sync', C.c_void_p)]
 
 
 # every symbol include/grand_b200.h declares: name -> (restype, argtypes)

@@ -30,6 +30,9 @@ int rhs_attention_impl(const grand_graph* g, const grand_attention* a, const flo
                        const grand_epilogue* ep, bool project, cudaStream_t stream);
 int rhs_laplacian_impl(const grand_graph* g, int d, const float* x, const float* w_csr, const grand_workspace* ws,
                        const grand_epilogue* ep, cudaStream_t stream);
+int integrate_fixed_coop_entry(const grand_graph* g, const grand_attention* a, const float* w_csr, int d,
+                               const grand_workspace* ws, const grand_epilogue* residual, int method, const float* dt,
+                               int n_steps, float* y, float* stage_buffers, cudaStream_t stream);
 int attention_weights_impl(const grand_graph* g, const grand_attention* a, const float* x, const grand_workspace* ws,
                            float* attention_out, float* prods_out, float* mean_csr_out, cudaStream_t stream);
 int edge_values_to_csr_impl(const grand_graph* g, const float* w, int heads, float* w_csr, cudaStream_t stream);
@@ -477,6 +480,12 @@ int grand_integrate_fixed(const grand_graph* g, const grand_attention* a, const 
   GRAND_REQUIRE(g->n_cols == g->n_rows, GRAND_EUNSUPPORTED,
                 "integrate_fixed: sharded graphs need a halo exchange between stages; drive the stages from the host");
   cudaStream_t stream = (cudaStream_t)stream_;
+  {
+    // small graphs: the whole integration in ONE cooperative launch (csrc/rhs_coop.cu); anything it is not built for
+    // answers "unsupported" without an error and takes the per-evaluation path below
+    const int rc_coop = integrate_fixed_coop_entry(g, a, w_csr, d, ws, residual, method, dt, n_steps, y, stage_buffers, stream);
+    if (rc_coop != GRAND_EUNSUPPORTED) return rc_coop;
+  }
   const size_t plane = (size_t)g->n_cols * d;
   float* yb = stage_buffers;            // next-stage input
   float* yc = stage_buffers + plane;    // second scratch state

@@ -58,6 +58,13 @@ __device__ __forceinline__ int float_to_ordered(float f) {
 }
 __device__ __forceinline__ float ordered_to_float(int i) { return __int_as_float(i >= 0 ? i : i ^ 0x7fffffff); }
 
+#ifdef GRAND_COHERENT_LOADS
+// Translation units whose kernels REWRITE their inputs between grid-wide barriers (rhs_coop.cu: a whole integration in
+// one launch) must not use the non-coherent path: every state / Q / K load goes to L2 (ld.global.cg), which is where
+// the other blocks' stores of the previous stage are.
+__device__ __forceinline__ float4 ldg4(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ float4 ld_stream4(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }
+#else
 // 128-bit read-only gather load.  X/K rows are re-read by many warps: keep them in L1 (default policy).
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 // streaming accesses (touched once per kernel): do not pollute L1
@@ -68,6 +75,7 @@ __device__ __forceinline__ float4 ld_stream4(const float* p) {
                : "l"(p));
   return r;
 }
+#endif
 __device__ __forceinline__ void st_stream4(float* p, float4 v) {
   asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z),
                "f"(v.w));

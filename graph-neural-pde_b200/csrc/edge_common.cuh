@@ -139,6 +139,9 @@ __device__ __forceinline__ uint64_t policy_evict_normal() {
   return p;
 }
 __device__ __forceinline__ float4 ldg4_hint(const float* p, uint64_t policy) {
+#ifdef GRAND_COHERENT_LOADS
+  return __ldcg(reinterpret_cast<const float4*>(p));
+#endif
   float4 r;
   asm volatile("ld.global.nc.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
                : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
@@ -146,6 +149,9 @@ __device__ __forceinline__ float4 ldg4_hint(const float* p, uint64_t policy) {
   return r;
 }
 __device__ __forceinline__ float4 ld_stream4_hint(const float* p, uint64_t policy) {
+#ifdef GRAND_COHERENT_LOADS
+  return __ldcg(reinterpret_cast<const float4*>(p));
+#endif
   float4 r;
   asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
                : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
@@ -164,6 +170,11 @@ struct float8 {
 };
 __device__ __forceinline__ float8 ldg8(const float* p) {
   float8 r;
+#ifdef GRAND_COHERENT_LOADS
+  r.lo = __ldcg(reinterpret_cast<const float4*>(p));
+  r.hi = __ldcg(reinterpret_cast<const float4*>(p) + 1);
+  return r;
+#endif
   asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                : "=f"(r.lo.x), "=f"(r.lo.y), "=f"(r.lo.z), "=f"(r.lo.w), "=f"(r.hi.x), "=f"(r.hi.y), "=f"(r.hi.z),
                  "=f"(r.hi.w)

@@ -373,6 +373,39 @@ int rhs_attention_impl(const grand_graph* g, const grand_attention* a, const flo
   return launch_rhs_mode(MODE_PRECOMP, A, stream);
 }
 
+int integrate_fixed_coop(const RhsArgs& A, bool attention, const grand_attention* a, int method, const float* dt, int n_steps,
+                         float* y, float* stage_buffers, int* sync, cudaStream_t stream);
+
+// Small graphs: the whole fixed-grid integration as one cooperative launch (csrc/rhs_coop.cu).  GRAND_EUNSUPPORTED (no
+// error message) = "not for this kernel", the caller falls back to one launch group per evaluation.
+int integrate_fixed_coop_entry(const grand_graph* g, const grand_attention* a, const float* w_csr, int d,
+                               const grand_workspace* ws, const grand_epilogue* residual, int method, const float* dt,
+                               int n_steps, float* y, float* stage_buffers, cudaStream_t stream) {
+  if (ws == nullptr || ws->coop_sync == nullptr || residual->peers != nullptr || residual->coef_dev != nullptr) return GRAND_EUNSUPPORTED;
+  if (check_graph(g) != GRAND_OK) return GRAND_EUNSUPPORTED;
+  RhsArgs A;
+  memset(&A, 0, sizeof(A));
+  A.g = view(g);
+  A.d = d;
+  if (a != nullptr) {
+    if (make_attn_view(a, &A.a) != GRAND_OK || ws->q == nullptr || ws->k == nullptr) return GRAND_EUNSUPPORTED;
+    if (a->edge_weight_csr != nullptr && false) return GRAND_EUNSUPPORTED;
+    A.q = ws->q; A.k = ws->k;
+  } else {
+    if (w_csr == nullptr) return GRAND_EUNSUPPORTED;
+    A.w_csr = w_csr;
+  }
+  grand_epilogue ep0;
+  memset(&ep0, 0, sizeof(ep0));
+  ep0.alpha_train = residual->alpha_train; ep0.beta_train = residual->beta_train; ep0.x0 = residual->x0;
+  ep0.no_alpha_sigmoid = residual->no_alpha_sigmoid;
+  if (ep0.alpha_train == nullptr || (ep0.x0 != nullptr && ep0.beta_train == nullptr)) return GRAND_EUNSUPPORTED;
+  A.ep = view(&ep0);
+  A.lrow_stats = ws->lrow_stats; A.lpartial = ws->lpartial; A.lcounter = ws->lcounter;
+  A.l2_hints = 0;
+  return integrate_fixed_coop(A, a != nullptr, a, method, dt, n_steps, y, stage_buffers, ws->coop_sync, stream);
+}
+
 int rhs_attention_backward_impl(const grand_graph* g, const grand_attention* a, const float* x, const float* grad_f,
                                 const grand_workspace* ws, const float* alpha_train, int no_alpha_sigmoid,
                                 float* row_dot, float* abar_out, float* dq, float* dk, GraphView gv,

@@ -93,6 +93,7 @@ __device__ __forceinline__ float sseg_sum(float v, int room, int lo) {
   return __shfl_sync(kFull, v, lo);
 }
 
+#ifndef GRAND_STREAM_DEVICE_ONLY
 // ---- long rows: softmax statistics (max, sum-exp) per head of every long SEGMENT, one block per segment; the segments
 //      of a row merge their row's pairs themselves (<= deg / seg_edges pairs per head) --------------------------------
 __global__ void __launch_bounds__(kStatsThreads)
@@ -161,6 +162,8 @@ lseg_stats_kernel(GraphView g, AttnView a, const float* __restrict__ q, const fl
     }
   }
 }
+
+#endif  // GRAND_STREAM_DEVICE_ONLY
 
 // ---- epilogue operands of one row, requested BEFORE the row's neighbours are gathered -----------------------------------
 // Named members, every access statically indexed and written under the same warp-uniform conditions it is read under:
@@ -388,7 +391,7 @@ __device__ __forceinline__ void merge_pairs(float& m, float& l) {
 }
 
 // ---- a whole medium row or a segment of a long row: cnt edges of ONE row from CSR position beg ----------------------------
-template <int MODE, bool FULL, int R, int HM>
+template <int MODE, bool FULL, int R, int HM, bool STATS = false>
 __device__ __forceinline__ void process_segment(const RhsArgs& A, const int4 desc, int unit, int lane, float alpha,
                                                 float beta, uint64_t pol_keep, uint64_t pol_stream) {
   constexpr int NB = (GRAND_STREAM_BATCH / R) < 2 ? 2 : (GRAND_STREAM_BATCH / R);
@@ -402,14 +405,14 @@ __device__ __forceinline__ void process_segment(const RhsArgs& A, const int4 des
 #pragma unroll
   for (int h = 0; h < HM; ++h) { m[h] = -INFINITY; l[h] = 0.f; }
   if (MODE == MODE_FUSED) {
-    if (split >= 0) {
+    if (split >= 0 && !STATS) {
       // the row's softmax statistics: merge the (max, sum-exp) pairs of all its segments (pre-pass lseg_stats_kernel)
       const int slot0 = __ldg(A.g.lrow_slot0 + split), slot1 = __ldg(A.g.lrow_slot0 + split + 1);
 #pragma unroll
       for (int h = 0; h < HM; ++h) {
         if (h < H) {
           for (int u = slot0 + lane; u < slot1; u += kWarp) {
-            const float2 pr = __ldg(reinterpret_cast<const float2*>(A.lrow_stats) + (size_t)u * H + h);
+            const float2 pr = __ldcg(reinterpret_cast<const float2*>(A.lrow_stats) + (size_t)u * H + h);
             const float mn = fmaxf(m[h], pr.x);
             l[h] = l[h] * expf(m[h] - mn) + pr.y * expf(pr.x - mn);
             m[h] = mn;
@@ -452,6 +455,18 @@ __device__ __forceinline__ void process_segment(const RhsArgs& A, const int4 des
 #pragma unroll
       for (int h = 0; h < HM; ++h)
         if (h < H) merge_pairs(m[h], l[h]);
+    }
+    if (STATS) {   // statistics unit of a long segment (rhs_coop.cu, in-kernel pre-pass): publish (max, sum-exp), nothing else
+      if (lane == 0) {
+#pragma unroll
+        for (int h = 0; h < HM; ++h) {
+          if (h < H) {
+            __stcg(A.lrow_stats + ((size_t)unit * H + h) * 2 + 0, m[h]);
+            __stcg(A.lrow_stats + ((size_t)unit * H + h) * 2 + 1, l[h]);
+          }
+        }
+      }
+      return;
     }
   }
 
@@ -576,6 +591,7 @@ __device__ __forceinline__ void process_segment(const RhsArgs& A, const int4 des
   epi_finish<FULL, R>(A, rowoff, lane, alpha, beta, pol_stream, acc, E);
 }
 
+#ifndef GRAND_STREAM_DEVICE_ONLY
 // ---- the kernel -------------------------------------------------------------------------------------------------------
 template <int MODE, bool FULL, int R, int HM>
 __global__ void __launch_bounds__(kStreamThreads, R == 1 ? GRAND_STREAM_MINBLOCKS : 1)
@@ -679,5 +695,7 @@ int launch_stream_mode(int mode, const RhsArgs& A, cudaStream_t stream) {
   if (mode == MODE_PRECOMP) return launch_stream_mode_t<MODE_PRECOMP>(A, stream);
   return launch_stream_mode_t<MODE_WEIGHT>(A, stream);
 }
+
+#endif  // GRAND_STREAM_DEVICE_ONLY
 
 }  // namespace grand

@@ -104,7 +104,8 @@ class RhsEngine:
                 split_partial=f(p.n_split_tiles * self.d),
                 split_counter=torch.zeros(max(p.n_split_rows, 1), dtype=torch.int32, device=dev), gmax=f(1),
                 lrow_stats=f(p.n_lunits * max(heads, 1) * 2), lpartial=f(p.n_lunits * max(heads, 1) * self.d),
-                lcounter=torch.zeros(max(p.n_lrows, 1), dtype=torch.int32, device=dev))
+                lcounter=torch.zeros(max(p.n_lrows, 1), dtype=torch.int32, device=dev),
+                coop_sync=torch.zeros(4, dtype=torch.int32, device=dev))
     ws = N.GrandWorkspace()
     for name, t in keep.items():
       setattr(ws, name, t.data_ptr())
@@ -214,7 +215,15 @@ class RhsEngine:
   # ---- fixed-grid integration ------------------------------------------------------------------------------
   def integrate_fixed(self, spec, w_csr, residual_ep, method, dts, y, use_graph=True):
     """y <- y(t_end) in place (y is the persistent 'y' buffer).  One C call launches every stage; with `use_graph`
-    the launch sequence is captured once per (method, grid, buffers) and replayed."""
+    the launch sequence is captured once per (method, grid, buffers) and replayed.  Wrapped in an NVTX range
+    (`grand.integrate_fixed`) so that a timeline shows the solver spans."""
+    torch.cuda.nvtx.range_push('grand.integrate_fixed[%s x%d]' % (method, len(dts)))
+    try:
+      return self._integrate_fixed(spec, w_csr, residual_ep, method, dts, y, use_graph)
+    finally:
+      torch.cuda.nvtx.range_pop()
+
+  def _integrate_fixed(self, spec, w_csr, residual_ep, method, dts, y, use_graph=True):
     self._check_state(y, 'y')
     n_steps = len(dts)
     if n_steps == 0:

@@ -6,6 +6,8 @@ counts of the real graphs, symmetrised to directed COO; self loops are NOT inclu
 Also the reference's option dictionary with CLI defaults (reference src/run_GNN.py:282-436) for building `opt`
 directly, which is the only way to reach the BASELINE configs.
 """
+import os
+
 import numpy as np
 import torch
 
@@ -83,11 +85,25 @@ class Data:
 class SyntheticDataset:
   """`dataset.data`, `dataset.num_classes`, `dataset.num_features` like a PyG dataset."""
 
-  def __init__(self, name, seed=0, num_features=None):
+  def __init__(self, name, seed=0, num_features=None, root=None):
     n, m, maxdeg, feats, classes = DATASETS[name]
     feats = num_features or feats
     g = torch.Generator().manual_seed(seed)
-    edge_index = make_graph(n, m, maxdeg, seed)
+    self.source = 'synthetic'
+    edge_index = None
+    # real graph, if somebody put one next to the code (SURVEY.md 8(d)): <root>/<name>/edge_index.npy, int64 [2, E0],
+    # the dataset's directed edge list before self loops (what PyG's loader hands to the reference); nothing is downloaded
+    root = root or os.environ.get('GRAND_DATA_ROOT') or os.path.join(os.path.dirname(os.path.dirname(
+      os.path.abspath(__file__))), 'data')
+    path = os.path.join(root, name, 'edge_index.npy')
+    if os.path.exists(path):
+      ei = np.load(path)
+      if ei.ndim == 2 and ei.shape[0] == 2 and ei.size > 0:
+        edge_index = torch.from_numpy(np.ascontiguousarray(ei)).long()
+        n = int(edge_index.max()) + 1 if int(edge_index.max()) + 1 > n else n
+        self.source = path
+    if edge_index is None:
+      edge_index = make_graph(n, m, maxdeg, seed)
     x = torch.randn(n, feats, generator=g)
     y = torch.randint(0, classes, (n,), generator=g)
     perm = torch.randperm(n, generator=g)

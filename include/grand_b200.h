@@ -174,6 +174,8 @@ typedef struct grand_workspace {
   float* lrow_stats;           /* [n_lunits, heads, 2] softmax (max, sum-exp) of every long-row segment */
   float* lpartial;             /* [n_lunits, max(heads,1), d] partial sums of the long-row segments   */
   int32_t* lcounter;           /* [n_lrows], zero on first use; the kernel leaves it zero (atomicInc wraps) */
+  int32_t* coop_sync;          /* [4] zero on first use, or null: barrier words of the one-launch integration of small
+                                  graphs (csrc/rhs_coop.cu); null = always the per-evaluation launches          */
 } grand_workspace;
 
 int grand_abi_version(void);
