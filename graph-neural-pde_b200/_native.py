@@ -91,6 +91,9 @@ SIGNATURES = {
                                            C.POINTER(GrandWorkspace), C.POINTER(GrandEpilogue), _P]),
   'grand_rhs_attention_backward': (C.c_int, [C.POINTER(GrandGraph), C.POINTER(GrandAttention), _P, _P,
                                               C.POINTER(GrandWorkspace), _P, C.c_int32, _P, _P, _P, _P, _P]),
+  'grand_edge_dot': (C.c_int, [C.POINTER(GrandGraph), C.c_int32, _P, _P, _P, C.c_int32, _P, _P]),
+  'grand_attention_weights_backward': (C.c_int, [C.POINTER(GrandGraph), C.POINTER(GrandAttention), _P,
+                                                  C.POINTER(GrandWorkspace), _P, _P, _P, _P, _P]),
   'grand_rhs_laplacian': (C.c_int, [C.POINTER(GrandGraph), C.c_int32, _P, _P, C.POINTER(GrandWorkspace),
                                      C.POINTER(GrandEpilogue), _P]),
   'grand_attention_weights': (C.c_int, [C.POINTER(GrandGraph), C.POINTER(GrandAttention), _P,

@@ -157,6 +157,74 @@ class LaplacianRhsFn(torch.autograd.Function):
     return gx, dalpha, dbeta, None
 
 
+class FrozenAttentionFn(torch.autograd.Function):
+  """AttODEblock.get_attention_weights as a differentiable node (reference src/block_transformer_attention.py:28-39):
+  (x0, Wq, bq, Wk, bk) -> (attention[E, H] in caller order, not differentiable; mean_h attention[E] in CSR order,
+  differentiable).  The Laplacian function integrates with the second output (FrozenLaplacianRhsFn); its gradient sums
+  over the RHS evaluations and comes back here once: softmax backward at x0, then the dense tails."""
+
+  @staticmethod
+  def forward(ctx, x0, wq, bq, wk, bk, layer, eng):
+    x0 = x0.contiguous()
+    spec = layer.spec(eng)
+    if not spec.fused:
+      raise NotImplementedError('grand_b200 backward through frozen attention is built for attention_type=scaled_dot, '
+                                'softmax, attention_norm_idx=0')
+    att, _, mean_csr = eng.attention_weights(spec, x0, want_attention=True, want_prods=False, want_mean_csr=True)
+    ctx.layer, ctx.engine = layer, eng
+    ctx.save_for_backward(x0, wq, wk)
+    ctx.mark_non_differentiable(att)
+    return att, mean_csr
+
+  @staticmethod
+  def backward(ctx, _g_att, c_csr):
+    x0, wq, wk = ctx.saved_tensors
+    eng = ctx.engine
+    dq, dk = eng.attention_weights_backward(ctx.layer.spec(eng), x0, c_csr)
+    gx = dq @ wq + dk @ wk
+    return gx, dq.t() @ x0, dq.sum(0), dk.t() @ x0, dk.sum(0), None, None
+
+
+class FrozenLaplacianRhsFn(torch.autograd.Function):
+  """f = LaplacianODEFunc.forward(t, x) with differentiable per-edge weights `w_csr` (CSR order; the head mean of the
+  frozen attention).  `w_csr_t` is the same weight vector in the CSR order of the flipped graph (for A^T g)."""
+
+  @staticmethod
+  def forward(ctx, x, w_csr, alpha_train, beta_train, func, w_csr_t):
+    x = x.contiguous()
+    eng = func.engine(x)
+    f = torch.empty_like(x)
+    ep = func.residual_epilogue(eng, func.stage_x0(eng), f_out=f)
+    eng.rhs_laplacian(w_csr, x, ep)
+    ctx.func, ctx.engine, ctx.w_csr_t = func, eng, w_csr_t
+    ctx.x0 = func.x0 if func.opt['add_source'] else None
+    ctx.save_for_backward(x, w_csr, alpha_train, beta_train)
+    return f
+
+  @staticmethod
+  def backward(ctx, g):
+    x, w_csr, alpha_train, beta_train = ctx.saved_tensors
+    func = ctx.func
+    opt = func.opt
+    g = g.contiguous()
+    no_sig = bool(opt['no_alpha_sigmoid'])
+    eng = _same_engine(ctx, func, x)
+    eng_t = _transposed_engine(func, x)
+    gx = torch.empty_like(x)
+    ep_t = RhsEngine.epilogue(alpha_train.detach(), None, None, no_sig, f_out=gx)
+    eng_t.rhs_laplacian(ctx.w_csr_t, g, ep_t)
+    gw = eng.edge_dot(x, g, alpha_train.detach(), no_sig) if ctx.needs_input_grad[1] else None
+    dalpha = dbeta = None
+    if ctx.needs_input_grad[2]:
+      r = torch.empty_like(x)
+      ep_r = RhsEngine.epilogue(_ConstOne.get(x.device), None, None, True, f_out=r)
+      eng.rhs_laplacian(w_csr, x, ep_r)
+      dalpha = (g * r).sum() * _sigmoid_grad(alpha_train.detach(), no_sig)
+    if ctx.needs_input_grad[3] and opt['add_source']:
+      dbeta = (g * ctx.x0).sum()
+    return gx, gw, dalpha, dbeta, None, None
+
+
 def needs_grad(func, *tensors):
   if not torch.is_grad_enabled():
     return False

@@ -25,8 +25,29 @@ class AttODEblock(ODEblock):
     attention, _ = self.multihead_att_layer(x, self.odefunc.edge_index, engine=self.odefunc.engine(x))
     return attention
 
+  def _differentiable_attention(self, x):
+    """Training without the adjoint: the reference backpropagates through the frozen attention into the block's Q / K
+    and into x(0) (autograd over :28-39).  -> attention [E, H]; leaves (mean_csr with history, flipped-order copy) on
+    the function.  Under the adjoint the reference's torchdiffeq only differentiates the function's own parameters, so
+    the frozen weights are constants there -- as here."""
+    from .autograd_rhs import FrozenAttentionFn, _transposed_engine
+    layer = self.multihead_att_layer
+    if not hasattr(layer, 'Q'):
+      raise NotImplementedError('grand_b200 backward: the beltrami exp_kernel layer is forward-only')
+    eng = self.odefunc.engine(x)
+    frozen, mean_csr = FrozenAttentionFn.apply(x, layer.Q.weight, layer.Q.bias, layer.K.weight, layer.K.bias, layer, eng)
+    eng_t = _transposed_engine(self.odefunc, x)
+    self.odefunc.frozen_weights = (mean_csr, eng_t.edge_values_to_csr(frozen))
+    return frozen
+
   def forward(self, x):
-    frozen = self.get_attention_weights(x)
+    self.odefunc.frozen_weights = None
+    wants_grad = torch.is_grad_enabled() and (x.requires_grad or any(
+      p.requires_grad for p in self.multihead_att_layer.parameters()))
+    if wants_grad and not (self.opt['adjoint'] and self.training):
+      frozen = self._differentiable_attention(x)
+    else:
+      frozen = self.get_attention_weights(x.detach())
     self.odefunc.attention_weights = frozen
     self.reg_odefunc.odefunc.attention_weights = frozen
     o = self.opt

@@ -30,6 +30,11 @@ int rhs_attention_impl(const grand_graph* g, const grand_attention* a, const flo
                        const grand_epilogue* ep, bool project, cudaStream_t stream);
 int rhs_laplacian_impl(const grand_graph* g, int d, const float* x, const float* w_csr, const grand_workspace* ws,
                        const grand_epilogue* ep, cudaStream_t stream);
+int edge_dot_impl(const grand_graph* g, int d, const float* x, const float* grad, const float* alpha_train,
+                  int no_alpha_sigmoid, float* c_out, cudaStream_t stream);
+int attention_weights_backward_host(const grand_graph* g, const grand_attention* a, const float* x0,
+                                    const grand_workspace* ws, const float* c_csr, float* row_dot, float* dq, float* dk,
+                                    cudaStream_t stream);
 int integrate_fixed_coop_entry(const grand_graph* g, const grand_attention* a, const float* w_csr, int d,
                                const grand_workspace* ws, const grand_epilogue* residual, int method, const float* dt,
                                int n_steps, float* y, float* stage_buffers, cudaStream_t stream);
@@ -233,6 +238,18 @@ int grand_rhs_attention_backward(const grand_graph* g, const grand_attention* a,
   GRAND_REQUIRE(a && a->wq && a->bq && a->wk && a->bk, GRAND_EINVAL, "rhs_attention_backward: null attention weights");
   return rhs_attention_backward_host(g, a, x, grad_f, ws, alpha_train, no_alpha_sigmoid, row_dot, abar_out, dq, dk,
                                      (cudaStream_t)stream);
+}
+
+int grand_edge_dot(const grand_graph* g, int32_t d, const float* x, const float* grad_f, const float* alpha_train,
+                   int32_t no_alpha_sigmoid, float* c_csr_out, void* stream) {
+  return edge_dot_impl(g, d, x, grad_f, alpha_train, no_alpha_sigmoid, c_csr_out, (cudaStream_t)stream);
+}
+
+int grand_attention_weights_backward(const grand_graph* g, const grand_attention* a, const float* x0,
+                                     const grand_workspace* ws, const float* c_csr, float* row_dot, float* dq, float* dk,
+                                     void* stream) {
+  GRAND_REQUIRE(a && a->wq && a->bq && a->wk && a->bk, GRAND_EINVAL, "attention_weights_backward: null attention weights");
+  return attention_weights_backward_host(g, a, x0, ws, c_csr, row_dot, dq, dk, (cudaStream_t)stream);
 }
 
 int grand_rhs_laplacian(const grand_graph* g, int32_t d, const float* x, const float* w_csr, const grand_workspace* ws,

@@ -409,7 +409,7 @@ int integrate_fixed_coop_entry(const grand_graph* g, const grand_attention* a, c
 int rhs_attention_backward_impl(const grand_graph* g, const grand_attention* a, const float* x, const float* grad_f,
                                 const grand_workspace* ws, const float* alpha_train, int no_alpha_sigmoid,
                                 float* row_dot, float* abar_out, float* dq, float* dk, GraphView gv,
-                                cudaStream_t stream);
+                                cudaStream_t stream, const float* c_in);
 
 int rhs_attention_backward_host(const grand_graph* g, const grand_attention* a, const float* x, const float* grad_f,
                                 const grand_workspace* ws, const float* alpha_train, int no_alpha_sigmoid,
@@ -436,7 +436,77 @@ int rhs_attention_backward_host(const grand_graph* g, const grand_attention* a, 
     if ((rc = launch_split_stats(A, stream)) != GRAND_OK) return rc;
   }
   return rhs_attention_backward_impl(g, a, x, grad_f, ws, alpha_train, no_alpha_sigmoid, row_dot, abar_out, dq, dk,
-                                     A.g, stream);
+                                     A.g, stream, nullptr);
+}
+
+// ---- frozen attention (AttODEblock): dL/d(abar_e) accumulates over the whole integration, the softmax is differentiated
+//      once at x(0) ----------------------------------------------------------------------------------------------------
+// c[p] = alpha * grad_f[row_p] . x[col_p]  in CSR order: the gradient of one Laplacian RHS evaluation w.r.t. its per-edge
+// weights (f_i = alpha (sum_e w_e x_j - x_i) + ...).  One warp per row, the lanes split the state width.
+__global__ void __launch_bounds__(256)
+edge_dot_kernel(GraphView g, int d, const float* __restrict__ x, const float* __restrict__ grad,
+                const float* __restrict__ alpha_train, int no_alpha_sigmoid, float* __restrict__ c_out) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= g.n_rows) return;
+  float alpha = __ldg(alpha_train);
+  if (!no_alpha_sigmoid) alpha = 1.f / (1.f + expf(-alpha));
+  const int beg = __ldg(g.rowptr + row), end = __ldg(g.rowptr + row + 1);
+  const float* gi = grad + (size_t)row * d;
+  for (int p = beg; p < end; ++p) {
+    const float* xj = x + (size_t)__ldg(g.col + p) * d;
+    float s = 0.f;
+    if ((d & 3) == 0) {
+      for (int c = lane * 4; c < d; c += 128) {
+        const float4 a = ldg4(gi + c), b = ldg4(xj + c);
+        s = fmaf(a.x, b.x, s); s = fmaf(a.y, b.y, s); s = fmaf(a.z, b.z, s); s = fmaf(a.w, b.w, s);
+      }
+    } else {
+      for (int c = lane; c < d; c += 32) s = fmaf(__ldg(gi + c), __ldg(xj + c), s);
+    }
+    s = warp_sum(s);
+    if (lane == 0) c_out[p] = alpha * s;
+  }
+}
+
+int edge_dot_impl(const grand_graph* g, int d, const float* x, const float* grad, const float* alpha_train,
+                  int no_alpha_sigmoid, float* c_out, cudaStream_t stream) {
+  int rc;
+  if ((rc = check_graph(g)) != GRAND_OK) return rc;
+  GRAND_REQUIRE(d > 0 && x && grad && alpha_train && (c_out || g->n_edges == 0), GRAND_EINVAL, "edge_dot: null argument");
+  if (g->n_rows > 0 && g->n_edges > 0) {
+    edge_dot_kernel<<<(g->n_rows + 7) / 8, 256, 0, stream>>>(view(g), d, x, grad, alpha_train, no_alpha_sigmoid, c_out);
+    GRAND_CUDA_OK(cudaGetLastError());
+    count_launch();
+  }
+  return GRAND_OK;
+}
+
+// softmax + head-mean backward of SpGraphTransAttentionLayer.forward at x0, given c = dL/d(mean_h attention) in CSR order
+int attention_weights_backward_host(const grand_graph* g, const grand_attention* a, const float* x0,
+                                    const grand_workspace* ws, const float* c_csr, float* row_dot, float* dq, float* dk,
+                                    cudaStream_t stream) {
+  int rc;
+  if ((rc = check_graph(g)) != GRAND_OK) return rc;
+  GRAND_REQUIRE(a && x0 && ws && ws->q && ws->k && c_csr && dq && dk, GRAND_EINVAL, "attention_weights_backward: null argument");
+  GRAND_REQUIRE(g->n_cols == g->n_rows, GRAND_EUNSUPPORTED, "attention_weights_backward: sharded graphs are not built");
+  RhsArgs A;
+  memset(&A, 0, sizeof(A));
+  A.g = view(g);
+  if ((rc = make_attn_view(a, &A.a)) != GRAND_OK) return rc;
+  A.d = a->d;
+  A.x = x0; A.q = ws->q; A.k = ws->k;
+  A.split_stats = ws->split_stats; A.row_stats = ws->row_stats; A.split_partial = ws->split_partial;
+  A.split_counter = ws->split_counter;
+  rc = launch_project_qk(x0, g->n_rows, g->n_cols, a->d, a->wq, a->bq, a->wk, a->bk, A.a.ad_eff, ws->q, ws->k, stream);
+  if (rc != GRAND_OK) return rc;
+  if (g->n_split_tiles > 0) {
+    GRAND_REQUIRE(ws->split_stats && ws->row_stats && row_dot, GRAND_EINVAL,
+                  "attention_weights_backward: graph has long rows, workspace split arrays / row_dot are null");
+    if ((rc = launch_split_stats(A, stream)) != GRAND_OK) return rc;
+  }
+  // alpha is already inside c; the kernel still loads *alpha_train, so hand it any valid device float
+  return rhs_attention_backward_impl(g, a, x0, x0, ws, a->bq, 1, row_dot, nullptr, dq, dk, A.g, stream, c_csr);
 }
 
 int rhs_laplacian_impl(const grand_graph* g, int d, const float* x, const float* w_csr, const grand_workspace* ws,

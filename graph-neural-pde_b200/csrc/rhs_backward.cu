@@ -34,7 +34,9 @@ struct BwdArgs {
   const float* row_stats;   // [n_split_rows, H, 2] merged softmax statistics of long rows (forward pre-pass)
   float* row_dot;           // [n_split_rows, H] sum_e a_eh c_e of long rows (zero on entry)
   int phase;                // long rows need two passes: 0 accumulate row_dot, 1 use it; short rows only in phase 1
-  float* abar_out;          // [n_edges] caller order
+  const float* c_in;        // or null.  Non-null: dL/d(abar_e) is GIVEN ([n_edges], CSR order; frozen attention,
+                            // AttODEblock) instead of being formed as alpha grad_f_i . x_j: no staging, x / grad_f unused
+  float* abar_out;          // [n_edges] caller order, or null
   float* dq;                // [n_rows, ad]  (zero on entry)
   float* dk;                // [n_cols, ad]  (zero on entry)
 };
@@ -71,14 +73,16 @@ __global__ void __launch_bounds__(kBwdThreads, 2) rhs_attention_bwd_kernel(const
   float* gs = xs + (size_t)GRAND_TILE * d;
   const uint32_t bar = smem_u32(base + (GRAND_TILE + kBwdMaxRows) * row_bytes);
   const uint64_t pol = policy_evict_normal();
-  if (lane == 0) {
-    mbar_init(bar, 1);
-    mbar_expect_tx(bar, (uint32_t)((cnt + nrows) * row_bytes));
+  if (A.c_in == nullptr) {
+    if (lane == 0) {
+      mbar_init(bar, 1);
+      mbar_expect_tx(bar, (uint32_t)((cnt + nrows) * row_bytes));
+    }
+    __syncwarp();
+    if (valid) bulk_copy_g2s(smem_u32(xs) + lane * row_bytes, A.x + (size_t)j * d, (uint32_t)row_bytes, bar, pol);
+    if (lane < nrows)
+      bulk_copy_g2s(smem_u32(gs) + lane * row_bytes, A.grad_f + (size_t)(row0 + lane) * d, (uint32_t)row_bytes, bar, pol);
   }
-  __syncwarp();
-  if (valid) bulk_copy_g2s(smem_u32(xs) + lane * row_bytes, A.x + (size_t)j * d, (uint32_t)row_bytes, bar, pol);
-  if (lane < nrows)
-    bulk_copy_g2s(smem_u32(gs) + lane * row_bytes, A.grad_f + (size_t)(row0 + lane) * d, (uint32_t)row_bytes, bar, pol);
 
   // ---- attention a_eh of the lane's edge, as in the forward ----------------------------------------------------------
   float alpha = __ldg(A.alpha_train);
@@ -92,9 +96,13 @@ __global__ void __launch_bounds__(kBwdThreads, 2) rhs_attention_bwd_kernel(const
   const float inv_scale = A.a.inv_sqrt_dk_exact != 0.f ? A.a.inv_sqrt_dk_exact : 1.f / A.a.sqrt_dk;
 
   // ---- c_e = alpha * grad_f_i . x_j : every lane its own edge, skewed chunks --------------------------------------
-  mbar_wait(bar, 0);
   float c_e = 0.f;
-  if (valid) {
+  if (A.c_in != nullptr) {
+    if (valid) c_e = __ldg(A.c_in + beg + lane);
+  } else {
+    mbar_wait(bar, 0);
+  }
+  if (A.c_in == nullptr && valid) {
     const int chunks = d >> 2;
     const float* xr = xs + (size_t)lane * d;
     const float* gr = gs + (size_t)kk * d;
@@ -151,7 +159,7 @@ __global__ void __launch_bounds__(kBwdThreads, 2) rhs_attention_bwd_kernel(const
       }
     }
   }
-  if (A.phase == 1 && valid) A.abar_out[__ldg(A.g.eid + beg + lane)] = abar / (float)H;
+  if (A.phase == 1 && valid && A.abar_out != nullptr) A.abar_out[__ldg(A.g.eid + beg + lane)] = abar / (float)H;
 }
 
 int make_attn_view(const grand_attention* a, AttnView* out);
@@ -159,8 +167,9 @@ int make_attn_view(const grand_attention* a, AttnView* out);
 int rhs_attention_backward_impl(const grand_graph* g, const grand_attention* a, const float* x, const float* grad_f,
                                 const grand_workspace* ws, const float* alpha_train, int no_alpha_sigmoid,
                                 float* row_dot, float* abar_out, float* dq, float* dk, GraphView gv,
-                                cudaStream_t stream) {
+                                cudaStream_t stream, const float* c_in) {
   BwdArgs A;
+  A.c_in = c_in;
   A.g = gv;
   int rc = make_attn_view(a, &A.a);
   if (rc != GRAND_OK) return rc;
@@ -173,7 +182,7 @@ int rhs_attention_backward_impl(const grand_graph* g, const grand_attention* a, 
   A.alpha_train = alpha_train; A.no_alpha_sigmoid = no_alpha_sigmoid;
   A.row_stats = ws->row_stats; A.row_dot = row_dot;
   A.abar_out = abar_out; A.dq = dq; A.dk = dk;
-  const size_t smem = (size_t)kBwdWarps * ((size_t)(GRAND_TILE + kBwdMaxRows) * a->d * sizeof(float) + 16);
+  const size_t smem = c_in != nullptr ? 0 : (size_t)kBwdWarps * ((size_t)(GRAND_TILE + kBwdMaxRows) * a->d * sizeof(float) + 16);
   GRAND_REQUIRE(smem <= 227 * 1024, GRAND_EUNSUPPORTED, "rhs_attention_backward: state width %d needs %zu B of shared "
                 "memory per block", a->d, smem);
   if (smem > 48 * 1024)   // per device and cheap: set on every launch that needs it (no process-wide "already done" flag)

@@ -188,6 +188,32 @@ class RhsEngine:
       dk.data_ptr(), N.current_stream(dev)))
     return abar, dq, dk
 
+  def edge_dot(self, x, grad_f, alpha_train, no_alpha_sigmoid):
+    """c[p] = alpha grad_f[row_p] . x[col_p] in CSR order (grand_edge_dot): gradient of one Laplacian RHS evaluation
+    w.r.t. its per-edge weights."""
+    self._check_state(x)
+    self._check_state(grad_f, 'grad_f')
+    c = torch.empty((self.plan.n_edges,), dtype=torch.float32, device=self.device)
+    N.check(N.lib().grand_edge_dot(C.byref(self.plan.struct()), self.d, x.data_ptr(), grad_f.data_ptr(),
+                                   alpha_train.data_ptr(), 1 if no_alpha_sigmoid else 0, c.data_ptr(),
+                                   N.current_stream(self.device)))
+    return c
+
+  def attention_weights_backward(self, spec, x0, c_csr):
+    """Softmax + head-mean backward of the attention evaluated at x0, given c = dL/d(mean_h attention) in CSR order
+    (grand_attention_weights_backward): -> (dQ, dK)."""
+    self._check_state(x0, 'x0')
+    ws = self.workspace(spec)
+    p, dev = self.plan, self.device
+    dq = torch.zeros((p.n_rows, spec.ad_eff), dtype=torch.float32, device=dev)
+    dk = torch.zeros((p.n_cols, spec.ad_eff), dtype=torch.float32, device=dev)
+    row_dot = torch.zeros((max(p.n_split_rows, 1) * spec.heads,), dtype=torch.float32, device=dev)
+    c_csr = c_csr.contiguous()
+    N.check(N.lib().grand_attention_weights_backward(
+      C.byref(p.struct()), C.byref(spec.struct), x0.data_ptr(), C.byref(ws), c_csr.data_ptr(), row_dot.data_ptr(),
+      dq.data_ptr(), dk.data_ptr(), N.current_stream(dev)))
+    return dq, dk
+
   def edge_values_to_csr(self, w):
     N.require_cuda(w, 'edge values')
     w = w.contiguous()

@@ -7,7 +7,7 @@ import torch
 from torch import nn
 
 from . import _native as N
-from .autograd_rhs import LaplacianRhsFn, needs_grad
+from .autograd_rhs import FrozenLaplacianRhsFn, LaplacianRhsFn, needs_grad
 from .base_classes import ODEFunc
 from .engine import RhsEngine
 
@@ -26,6 +26,9 @@ class LaplacianODEFunc(ODEFunc):
     self.beta_sc = nn.Parameter(torch.ones(1))
     self._w_csr = None
     self._w_key = None
+    # AttODEblock in (non-adjoint) training: (mean_h attention in CSR order WITH autograd history, the same values in
+    # the flipped graph's CSR order); None otherwise
+    self.frozen_weights = None
 
   def edge_values(self):
     """Which tensor sparse_multiply would use (reference :28-36)."""
@@ -66,10 +69,9 @@ class LaplacianODEFunc(ODEFunc):
     self._bump_nfe()
     N.require_cuda(x, 'x')
     if needs_grad(self, x):
-      w = self.edge_values()
-      if w is not None and w.requires_grad:
-        raise NotImplementedError('grand_b200 backward: gradients through frozen attention weights (block=attention) '
-                                  'are not built; the constant block trains')
+      if self.frozen_weights is not None:
+        w_csr, w_csr_t = self.frozen_weights
+        return FrozenLaplacianRhsFn.apply(x, w_csr, self.alpha_train, self.beta_train, self, w_csr_t)
       return LaplacianRhsFn.apply(x, self.alpha_train, self.beta_train, self)
     x = x.contiguous()
     engine = self.engine(x)

@@ -218,6 +218,22 @@ int grand_rhs_attention_backward(const grand_graph* g, const grand_attention* a,
                                  const grand_workspace* ws, const float* alpha_train, int32_t no_alpha_sigmoid,
                                  float* row_dot, float* abar_out, float* dq, float* dk, void* stream);
 
+/* Gradients through FROZEN attention (AttODEblock, reference src/block_transformer_attention.py:36-39: the attention is
+ * evaluated once at x(0) and the Laplacian function integrates with its head mean).  The reference gets them from
+ * autograd; here
+ *   grand_edge_dot                     c[p] = alpha * grad_f[row_p] . x[col_p] (CSR order): the gradient of ONE Laplacian
+ *                                      RHS evaluation w.r.t. its per-edge weights; autograd sums it over the evaluations,
+ *   grand_attention_weights_backward   given that sum c = dL/d(mean_h attention) in CSR order: softmax + head-mean backward
+ *                                      of SpGraphTransAttentionLayer.forward at x0 -> dq [n_rows, ad], dk [n_cols, ad]
+ *                                      (zero on entry; dense tails dWq = dq^T x0 ... are GEMMs left to the caller).
+ *                                      row_dot: [n_split_rows, heads] scratch, zero on entry.  scaled_dot + softmax +
+ *                                      attention_norm_idx 0 only. */
+int grand_edge_dot(const grand_graph* g, int32_t d, const float* x, const float* grad_f, const float* alpha_train,
+                   int32_t no_alpha_sigmoid, float* c_csr_out, void* stream);
+int grand_attention_weights_backward(const grand_graph* g, const grand_attention* a, const float* x0,
+                                     const grand_workspace* ws, const float* c_csr, float* row_dot, float* dq, float* dk,
+                                     void* stream);
+
 /* One GRAND-l RHS evaluation: LaplacianODEFunc.forward (reference src/function_laplacian_diffusion.py:38-51);
  * `w_csr` is the per-edge weight sparse_multiply would use (:28-36) in CSR order. */
 int grand_rhs_laplacian(const grand_graph* g, int32_t d, const float* x, const float* w_csr, const grand_workspace* ws,

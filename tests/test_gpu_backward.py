@@ -121,6 +121,73 @@ def test_block_backward_vs_oracle_autograd(function, method):
                      [xo.grad] + [sd[k].grad for k in NAMES[function]], tol, ['x'] + NAMES[function])
 
 
+ATT_NAMES = ['multihead_att_layer.Q.weight', 'multihead_att_layer.Q.bias', 'multihead_att_layer.K.weight',
+             'multihead_att_layer.K.bias', 'odefunc.alpha_train', 'odefunc.beta_train']
+
+
+@pytest.mark.parametrize('method,max_degree', [('rk4', 150), ('euler', 1500), ('dopri5', 150)])
+def test_attention_block_backward_vs_oracle_autograd(method, max_degree):
+  """AttODEblock (GRAND-l): the attention is evaluated once at x(0) and frozen (reference
+  src/block_transformer_attention.py:36-39); without the adjoint its gradient reaches the block's Q / K and x(0)
+  through every RHS evaluation.  max_degree 1500 gives rows that are split across tiles in the backward kernel."""
+  from graph_neural_pde_b200.block_transformer_attention import AttODEblock
+  n, d, ad, heads = 1600 if max_degree > 1000 else 300, 32, 16, 4
+  edge_index = make_graph(n, 6 * n, max_degree=max_degree, seed=11)
+  torch.manual_seed(12)
+  x = torch.randn(n, d)
+  opt = default_opt(function='laplacian', block='attention', hidden_dim=d, attention_dim=ad, heads=heads, method=method,
+                    step_size=0.5, time=1.0, add_source=True, adjoint=False, tol_scale=1000.0)
+  data = Data(x=x, edge_index=edge_index, edge_attr=None, num_nodes=n)
+  block = AttODEblock(LaplacianODEFunc, (), opt, data, DEV, t=torch.tensor([0, opt['time']])).to(DEV)
+  g = torch.Generator().manual_seed(13)
+  with torch.no_grad():
+    for p_ in block.multihead_att_layer.parameters():
+      if p_.dim() == 2:
+        p_.copy_((1.5 * torch.randn(p_.shape, generator=g) / p_.shape[1] ** 0.5).to(DEV))
+      else:
+        p_.copy_((0.3 * torch.randn(p_.shape, generator=g)).to(DEV))
+    block.odefunc.alpha_train.fill_(0.3)
+    block.odefunc.beta_train.fill_(-0.4)
+  block.train()
+  xd = x.to(DEV).requires_grad_(True)
+  block.set_x0(x.to(DEV))
+  torch.manual_seed(3)
+  w = torch.randn(n, d)
+  z = block(xd)
+  (z * w.to(DEV)).sum().backward()
+  # oracle: autograd through attention_forward at x(0) + the integration, fp64
+  sd = _oracle_params(block)
+  xo = x.double().requires_grad_(True)
+  ei, ew = O.constant_block_graph(edge_index, None, n, {**opt, 'data_norm': 'rw'}, torch.float64)
+  att, _ = O.attention_forward(xo, ei, C.sub_state(sd, 'multihead_att_layer.'), opt, ew)
+  wts = O.laplacian_weights(opt, ew, att)
+  fo = lambda t, y: O.laplacian_rhs(y, ei, wts, opt, sd['odefunc.alpha_train'], sd['odefunc.beta_train'], x.double())
+  zo = O.block_forward(fo, xo, opt['time'], opt)
+  (zo * w.double()).sum().backward()
+  tol = 2e-2 if method == 'dopri5' else GTOL
+  C.assert_close(z, zo, 5e-3 if method == 'dopri5' else C.RTOL, 'z')
+  got = dict(block.named_parameters())
+  for k in ATT_NAMES[:3]:
+    assert got[k].grad is not None and float(got[k].grad.abs().max()) > 0, k
+  assert_grads_close([xd.grad] + [got[k].grad for k in ATT_NAMES], [xo.grad] + [sd[k].grad for k in ATT_NAMES], tol,
+                     ['x'] + ATT_NAMES)
+
+
+def test_run_gnn_trains_attention_block(capsys):
+  """run_GNN.main with --block attention --function laplacian (the paper's GRAND-l) trains: the start-up check lets
+  it through and the loss falls."""
+  from graph_neural_pde_b200 import run_GNN
+  args = run_GNN.build_parser().parse_args(['--dataset', 'Cora', '--function', 'laplacian', '--block', 'attention',
+                                            '--method', 'rk4', '--time', '1.0', '--step_size', '0.5', '--epoch', '6',
+                                            '--hidden_dim', '32', '--attention_dim', '16', '--heads', '4', '--lr', '0.02',
+                                            '--input_dropout', '0.0', '--quiet'])
+  torch.manual_seed(0)
+  run_GNN.main(vars(args))
+  out = capsys.readouterr().out
+  losses = [float(line.split('Loss ')[1].split(',')[0]) for line in out.splitlines() if line.startswith('Epoch:')]
+  assert len(losses) == 5 and losses[-1] < losses[0], losses
+
+
 def test_run_gnn_trains_end_to_end(capsys):
   """The reference's entry point (run_GNN.main) on the synthetic Cora stand-in: a few epochs of GRAND-nl with the
   default early-stopping model; the loss must fall and the attribute chain main() reads must be alive."""
