@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get('GRAND_LIB') or os.path.join(HERE, 'libgrand_b200.so')   # GRAND_LIB: A/B builds
 
 GRAND_TILE = 32
-GRAND_SEG_EDGES = int(os.environ.get('GRAND_SEG_EDGES', '256'))   # rows longer than this are cut into segments
+GRAND_SEG_EDGES = int(os.environ.get('GRAND_SEG_EDGES', '512'))   # rows longer than this are cut into segments
 GRAND_MAX_HEADS = 8
 GRAND_MAX_TERMS = 8
 ABI_VERSION = 2

@@ -102,6 +102,7 @@ __global__ void __launch_bounds__(kCoopThreads, 2) integrate_coop_kernel(const _
   __shared__ RhsArgs sA;
   __shared__ int s_next;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  NoRing no_ring;
   const int warps_per_block = kCoopThreads / kWarp;
   if (MODE == MODE_FUSED) {
     const int nw = C.base.a.ad_eff * C.base.d;
@@ -187,7 +188,7 @@ __global__ void __launch_bounds__(kCoopThreads, 2) integrate_coop_kernel(const _
             const int u = v * (int)gridDim.x + (int)blockIdx.x;
             if (u >= nL) break;
             const int4 desc = __ldg(A.g.seg_desc + u);
-            process_segment<MODE, FULL, R, HM, true>(A, desc, u, lane, alpha, beta, pol, pol);
+            process_segment<MODE, FULL, R, HM, true>(A, desc, u, lane, alpha, beta, pol, pol, no_ring);
           }
           __syncthreads();
           if (threadIdx.x == 0) s_next = 0;
@@ -204,7 +205,7 @@ __global__ void __launch_bounds__(kCoopThreads, 2) integrate_coop_kernel(const _
         if (u >= n_units) break;
         if (u < n_seg) {
           const int4 desc = __ldg(A.g.seg_desc + u);
-          process_segment<MODE, FULL, R, HM, false>(A, desc, u, lane, alpha, beta, pol, pol);
+          process_segment<MODE, FULL, R, HM, false>(A, desc, u, lane, alpha, beta, pol, pol, no_ring);
         } else {
           const int t = A.g.n_split_tiles + (u - n_seg);
           const int4 hdr = __ldg(A.g.win_hdr + t);

@@ -11,6 +11,8 @@
 //   counter, so the whole grid sweeps the (row-ordered) window list as one moving band: the streamed epilogue operands
 //   of neighbouring windows are touched at about the same time and the warps of a block balance dynamically.
 //
+//   (csrc/rhs_ring.cu is this kernel with the neighbour rows staged through shared memory by cp.async.bulk; it takes the
+//   attention modes for rows of <= 512 bytes, this file the rest and the fixed-weight mode.)
 //   Per unit: per-edge weights abar_e (MODE_FUSED: scaled_dot scores, row softmax, head mean -- reference
 //   src/function_transformer_attention.py:190-213, :34; MODE_PRECOMP / MODE_WEIGHT as rhs_window.cu), then per row ONE
 //   round trip: the row's epilogue operands (x_i, x0_i, stage-combine terms) and up to 8 neighbour rows are requested
@@ -289,6 +291,30 @@ __device__ __forceinline__ void gather_range(const float* __restrict__ xl, int d
   }
 }
 
+// d_k = 4, 4 heads: scores of the lane's edge from its Q / K rows (four float4 each), row softmax over the lanes
+// [lo, lo + room), head mean
+__device__ __forceinline__ float dk4_weight(const float4 (&qv)[4], const float4 (&kv)[4], bool valid, float ew, int room,
+                                            int lo) {
+  float s[4], m[4], ex[4], l[4];
+#pragma unroll
+  for (int h = 0; h < 4; ++h) {
+    float t = 0.f;
+    t = fmaf(qv[h].x, kv[h].x, t); t = fmaf(qv[h].y, kv[h].y, t);
+    t = fmaf(qv[h].z, kv[h].z, t); t = fmaf(qv[h].w, kv[h].w, t);
+    s[h] = valid ? (t * 0.5f) * ew : -INFINITY;   // / sqrt(4): exact; ew: reweight_attention :208-209
+  }
+#pragma unroll
+  for (int h = 0; h < 4; ++h) m[h] = sseg_max(s[h], room, lo);
+#pragma unroll
+  for (int h = 0; h < 4; ++h) ex[h] = valid ? attn_exp(s[h] - m[h]) : 0.f;
+#pragma unroll
+  for (int h = 0; h < 4; ++h) l[h] = sseg_sum(ex[h], room, lo);
+  float ab = 0.f;
+#pragma unroll
+  for (int h = 0; h < 4; ++h) ab += attn_div(ex[h], l[h]);
+  return ab * 0.25f;                               // / H, exact
+}
+
 // ---- per-edge weight of the lane's edge inside a packed window ----------------------------------------------------------
 template <int MODE>
 __device__ __forceinline__ float window_weight(const RhsArgs& A, int lane, int i, int j, int p, bool valid, int lo, int hi) {
@@ -321,23 +347,7 @@ __device__ __forceinline__ float window_weight(const RhsArgs& A, int lane, int i
       float4 qv[4], kv[4];
       load_row16(qi, qv);                    // idle lanes read row0's Q row and K row 0: harmless, no predicates
       load_row16(kj, kv);
-      float s[4], m[4], ex[4], l[4];
-#pragma unroll
-      for (int h = 0; h < 4; ++h) {
-        float t = 0.f;
-        t = fmaf(qv[h].x, kv[h].x, t); t = fmaf(qv[h].y, kv[h].y, t);
-        t = fmaf(qv[h].z, kv[h].z, t); t = fmaf(qv[h].w, kv[h].w, t);
-        s[h] = valid ? (t * 0.5f) * ew : -INFINITY;   // / sqrt(4): exact; ew: reweight_attention :208-209
-      }
-#pragma unroll
-      for (int h = 0; h < 4; ++h) m[h] = sseg_max(s[h], room, lo);
-#pragma unroll
-      for (int h = 0; h < 4; ++h) ex[h] = valid ? attn_exp(s[h] - m[h]) : 0.f;
-#pragma unroll
-      for (int h = 0; h < 4; ++h) l[h] = sseg_sum(ex[h], room, lo);
-#pragma unroll
-      for (int h = 0; h < 4; ++h) ab += attn_div(ex[h], l[h]);
-      ab *= 0.25f;                                     // / H, exact
+      ab = dk4_weight(qv, kv, valid, ew, room, lo);
     } else {
       for (int h = 0; h < H; ++h) {
         float s = -INFINITY;
@@ -390,10 +400,20 @@ __device__ __forceinline__ void merge_pairs(float& m, float& l) {
   m = mm;
 }
 
+// where the neighbour rows of a 32-edge chunk come from: NoRing = straight into registers (gather_range, this file);
+// csrc/rhs_ring.cu passes its per-warp shared-memory stage fed by cp.async.bulk
+struct NoRing {
+  static constexpr bool enabled = false;
+  __device__ __forceinline__ void issue(const float*, int, int, bool, int, int, uint64_t) {}
+  __device__ __forceinline__ void wait() {}
+  template <bool FULL>
+  __device__ __forceinline__ void accumulate(float, int, int, int, int, float (&)[4]) {}
+};
+
 // ---- a whole medium row or a segment of a long row: cnt edges of ONE row from CSR position beg ----------------------------
-template <int MODE, bool FULL, int R, int HM, bool STATS = false>
+template <int MODE, bool FULL, int R, int HM, bool STATS = false, class RING = NoRing>
 __device__ __forceinline__ void process_segment(const RhsArgs& A, const int4 desc, int unit, int lane, float alpha,
-                                                float beta, uint64_t pol_keep, uint64_t pol_stream) {
+                                                float beta, uint64_t pol_keep, uint64_t pol_stream, RING& ring) {
   constexpr int NB = (GRAND_STREAM_BATCH / R) < 2 ? 2 : (GRAND_STREAM_BATCH / R);
   const int d = A.d;
   const int row = desc.x, beg = desc.y, cnt = desc.z, split = desc.w;
@@ -484,6 +504,7 @@ __device__ __forceinline__ void process_segment(const RhsArgs& A, const int4 des
     const bool valid = lane < nvalid;
     const int p = beg + c0 + lane;
     const int j = jn;
+    if (RING::enabled) ring.issue(A.x, d, j, valid, nvalid, lane, pol_keep);   // the chunk's rows fly while it is scored
     if (c0 + kWarp < cnt) jn = (c0 + kWarp + lane < cnt) ? __ldg(A.g.col + p + kWarp) : 0;
     float ab = 0.f;
     if (MODE == MODE_WEIGHT) {
@@ -528,8 +549,13 @@ __device__ __forceinline__ void process_segment(const RhsArgs& A, const int4 des
       }
     }
     if (split < 0 && c0 + kWarp >= cnt) epi_load<FULL, R>(A, rowoff, lane, pol_stream, E);   // with the last chunk's gathers
-    const unsigned joff = (unsigned)j * (unsigned)d;
-    gather_range<FULL, R, NB>(xl, d, lane, joff, ab, 0, nvalid, pol_keep, acc);
+    if (RING::enabled) {
+      ring.wait();
+      ring.template accumulate<FULL>(ab, 0, nvalid, d, lane, acc[0]);
+    } else {
+      const unsigned joff = (unsigned)j * (unsigned)d;
+      gather_range<FULL, R, NB>(xl, d, lane, joff, ab, 0, nvalid, pol_keep, acc);
+    }
   }
 
   if (split < 0) {
@@ -624,6 +650,7 @@ rhs_stream_kernel(const __grid_constant__ RhsArgs A) {
     }
   };
 
+  NoRing no_ring;
   int u = grab();
   int4 h4 = make_int4(0, 0, 0, 0);
   int2 rec = make_int2(0, 0);
@@ -633,7 +660,7 @@ rhs_stream_kernel(const __grid_constant__ RhsArgs A) {
     int4 h4n = make_int4(0, 0, 0, 0);
     int2 recn = make_int2(0, 0);
     fetch(un, h4n, recn);
-    if (u < n_seg) process_segment<MODE, FULL, R, HM>(A, h4, u, lane, alpha, beta, pol_keep, pol_stream);
+    if (u < n_seg) process_segment<MODE, FULL, R, HM>(A, h4, u, lane, alpha, beta, pol_keep, pol_stream, no_ring);
     else process_window<MODE, FULL, R>(A, h4, rec, lane, alpha, beta, pol_keep, pol_stream);
     u = un;
     h4 = h4n;
@@ -682,7 +709,11 @@ bool stream_kernel_ok(const RhsArgs& A) {
   return true;
 }
 
+bool ring_kernel_ok(int mode, const RhsArgs& A);      // csrc/rhs_ring.cu: the same work list with TMA-staged neighbour rows
+int launch_ring_mode(int mode, const RhsArgs& A, cudaStream_t stream);
+
 int launch_stream_mode(int mode, const RhsArgs& A, cudaStream_t stream) {
+  const bool ring = ring_kernel_ok(mode, A);
   if (mode == MODE_FUSED) {
     if (A.g.n_lunits > 0) {
       GRAND_REQUIRE(A.lrow_stats != nullptr, GRAND_EINVAL, "graph has long rows: workspace lrow_stats is null");
@@ -690,8 +721,9 @@ int launch_stream_mode(int mode, const RhsArgs& A, cudaStream_t stream) {
       GRAND_CUDA_OK(cudaGetLastError());
       count_launch();
     }
-    return launch_stream_mode_t<MODE_FUSED>(A, stream);
+    return ring ? launch_ring_mode(mode, A, stream) : launch_stream_mode_t<MODE_FUSED>(A, stream);
   }
+  if (ring) return launch_ring_mode(mode, A, stream);
   if (mode == MODE_PRECOMP) return launch_stream_mode_t<MODE_PRECOMP>(A, stream);
   return launch_stream_mode_t<MODE_WEIGHT>(A, stream);
 }

@@ -116,7 +116,8 @@ class GraphPlan:
     #      partial sums are merged by the last segment to finish).  Longest first: the tail of the kernel is made of the
     #      small packed windows.
     if seg_edges is None:
-      # Large graphs: a warp takes a whole row of up to 256 in-edges (fewer partial sums, no statistics pre-pass for them).
+      # Large graphs: a warp takes a whole row of up to 512 in-edges (fewer partial sums, no statistics pre-pass for them;
+      # ogbn-arxiv, TMA-ring kernel: 64 -> 362, 128 -> 288, 256 -> 265, 512 -> 254, 1024 -> 257, 2048 -> 296 us per launch).
       # Small graphs (everything L2-resident, a handful of units per warp): the launch lasts as long as its longest unit,
       # so long rows are cut finer and spread over more warps (measured on B200: Photo 165 -> 115 us per evaluation, Cora
       # 56 -> 46 with 64-edge segments; ogbn-arxiv 342 us with 256 against 376 us with 128, profiles/README.md).
