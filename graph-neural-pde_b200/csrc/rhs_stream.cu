@@ -432,7 +432,14 @@ __device__ __forceinline__ void process_segment(const RhsArgs& A, const int4 des
       for (int h = 0; h < HM; ++h) {
         if (h < H) {
           for (int u = slot0 + lane; u < slot1; u += kWarp) {
+            // written by the pre-pass kernel of an EARLIER launch: the read-only path is fine (and keeps this kernel's
+            // register allocation free of spills: with ld.global.cg here ptxas spills 128 bytes of the window path);
+            // only the one-launch integration (rhs_coop.cu) writes these pairs inside the same launch
+#ifdef GRAND_COHERENT_LOADS
             const float2 pr = __ldcg(reinterpret_cast<const float2*>(A.lrow_stats) + (size_t)u * H + h);
+#else
+            const float2 pr = __ldg(reinterpret_cast<const float2*>(A.lrow_stats) + (size_t)u * H + h);
+#endif
             const float mn = fmaxf(m[h], pr.x);
             l[h] = l[h] * expf(m[h] - mn) + pr.y * expf(pr.x - mn);
             m[h] = mn;
