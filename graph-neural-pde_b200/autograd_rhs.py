@@ -365,14 +365,121 @@ class OdeintAdjointFn(torch.autograd.Function):
       state = [y, a] + g_params
       state = _integrate_system(aug_dynamics, state, t[i], t[i - 1], method, ctx.adjoint_options, ctx.adjoint_rtol,
                                 ctx.adjoint_atol)
-      y, a, g_params = state[0], state[1], state[2:]
+      a, g_params = state[1], state[2:]
+      y = sol[i - 1]                      # torchdiffeq: "update to use our forward-pass estimate of the state"
       a = a + grad_sol[i - 1]
     return (a, None, None, None, None, None, None, None) + tuple(g_params)
+
+
+# torchdiffeq 0.2.1's adaptive Runge-Kutta family (rk_common.py / dopri5.py / bosh3.py / adaptive_heun.py): order, stage
+# rows, solution / error / mid-point weights.  `adaptive_heun` is the reference's default adjoint method
+# (reference src/run_GNN.py:334), `dopri5` what its Computers configuration uses (src/best_params.py).
+ADAPTIVE_TABLEAUS = {
+  'dopri5': dict(order=5, alpha=[1 / 5, 3 / 10, 4 / 5, 8 / 9, 1., 1.], beta=DP_BETA, c_sol=DP_BETA[-1] + [0.],
+                 c_error=DP_C_ERROR, c_mid=DP_C_MID),
+  'bosh3': dict(order=3, alpha=[1 / 2, 3 / 4, 1.], beta=[[1 / 2], [0., 3 / 4], [2 / 9, 1 / 3, 4 / 9]],
+                c_sol=[2 / 9, 1 / 3, 4 / 9, 0.], c_error=[2 / 9 - 7 / 24, 1 / 3 - 1 / 4, 4 / 9 - 1 / 3, -1 / 8],
+                c_mid=[0., 0.5, 0., 0.]),
+  'adaptive_heun': dict(order=2, alpha=[1.], beta=[[1.]], c_sol=[0.5, 0.5], c_error=[0.5, -0.5], c_mid=[0.5, 0.]),
+}
+
+
+def _mixed_norm(parts):
+  """torchdiffeq's default norm of a tuple state: max over the components of their RMS norms (ONE host read)."""
+  return float(torch.stack([_rms(p) for p in parts]).max())
+
+
+def _lin(base, dt, coefs, ks):
+  """base + dt * sum_j coefs[j] * ks[j] for a list-of-tensors state (zero weights skipped)."""
+  out = []
+  for c in range(len(base)):
+    acc = base[c]
+    for w, k in zip(coefs, ks):
+      if w != 0:
+        acc = acc + (dt * w) * k[c]
+    out.append(acc)
+  return out
+
+
+def integrate_system_adaptive(f, state, ta, tb, method, rtol, atol, first_step=None, max_num_steps=2 ** 31 - 1,
+                              stats=None):
+  """RKAdaptiveStepsizeODESolver.integrate over [ta, tb] for a list-of-tensors state, returning the state at tb
+  (torchdiffeq 0.2.1 semantics: Hairer initial step with `order - 1`, error ratio in the mixed norm, step factor
+  clipped to [0.2, 10] with safety 0.9, the last step overshoots tb and the quartic Hermite fit through
+  (y0, y_mid, y1, f0, f1) is evaluated at tb).  tb < ta integrates the time-reversed system, as `_check_inputs` does for a
+  decreasing `t`.  As in the library, the derivative handed to the next step is the LAST STAGE's (`f1 = k[..., -1]`),
+  also for tableaus that are not first-same-as-last (adaptive_heun)."""
+  tab = ADAPTIVE_TABLEAUS[method]
+  order, betas = tab['order'], tab['beta']
+  fsal = tab['c_sol'][-1] == 0 and list(tab['c_sol'][:-1]) == list(betas[-1])
+  sign = 1.0 if tb >= ta else -1.0
+  s0, s1 = sign * ta, sign * tb
+
+  def g(s, st):
+    ks = f(sign * s, st)
+    return ks if sign > 0 else [-k for k in ks]
+
+  n_eval = 1
+  f0 = g(s0, state)
+  if first_step is None:
+    scale = [atol + y.abs() * rtol for y in state]
+    d0 = _mixed_norm([y / sc for y, sc in zip(state, scale)])
+    d1 = _mixed_norm([k / sc for k, sc in zip(f0, scale)])
+    h0 = 1e-6 if (d0 < 1e-5 or d1 < 1e-5) else 0.01 * d0 / d1
+    f1 = g(s0 + h0, [y + h0 * k for y, k in zip(state, f0)])
+    n_eval += 1
+    d2 = _mixed_norm([(b - a) / sc for a, b, sc in zip(f0, f1, scale)]) / h0
+    h1 = max(1e-6, h0 * 1e-3) if (d1 <= 1e-15 and d2 <= 1e-15) else (0.01 / max(d1, d2)) ** (1.0 / order)
+    dt = min(100 * h0, h1)
+  else:
+    dt = float(first_step)
+  y, t0, t1 = state, s0, s0
+  interp = None
+  n_steps = 0
+  while s1 > t1:
+    assert n_steps < max_num_steps, 'max_num_steps exceeded ({}>={})'.format(n_steps, max_num_steps)
+    assert t1 + dt > t1, 'underflow in dt {}'.format(dt)
+    ks = [f0]
+    yi = y
+    for alpha_i, beta_i in zip(tab['alpha'], betas):
+      yi = _lin(y, dt, beta_i, ks)
+      ks.append(g(t1 + dt if alpha_i == 1. else t1 + alpha_i * dt, yi))
+      n_eval += 1
+    y1 = yi if fsal else _lin(y, dt, tab['c_sol'], ks)
+    err = _lin([torch.zeros_like(p) for p in y], dt, tab['c_error'], ks)
+    ratio = _mixed_norm([e / (atol + rtol * torch.max(a.abs(), b.abs())) for e, a, b in zip(err, y, y1)])
+    n_steps += 1
+    if ratio <= 1:
+      y_mid = _lin(y, dt, tab['c_mid'], ks)
+      interp = (t1, t1 + dt, y, y1, y_mid, ks[0], ks[-1], dt)
+      y, f0, t0, t1 = y1, ks[-1], t1, t1 + dt
+    if ratio == 0:
+      dt = dt * 10.0
+    else:
+      dt = dt * min(10.0, max(0.9 / ratio ** (1.0 / order), 1.0 if ratio < 1 else 0.2))
+  if stats is not None:
+    stats['n_eval'], stats['n_steps'] = n_eval, n_steps
+  if interp is None:
+    return list(state)
+  ia, ib, ya, yb, ym, fa, fb, h = interp
+  if s1 == ib:
+    return list(yb)
+  x = (s1 - ia) / (ib - ia)
+  out = []
+  for c in range(len(ya)):
+    a = 2 * h * (fb[c] - fa[c]) - 8 * (yb[c] + ya[c]) + 16 * ym[c]
+    b = h * (5 * fa[c] - 3 * fb[c]) + 18 * ya[c] + 14 * yb[c] - 32 * ym[c]
+    cc = h * (fb[c] - 4 * fa[c]) - 11 * ya[c] - 5 * yb[c] + 16 * ym[c]
+    out.append(ya[c] + x * (h * fa[c]) + x ** 2 * cc + x ** 3 * b + x ** 4 * a)
+  return out
 
 
 def _integrate_system(f, state, ta, tb, method, options, rtol, atol):
   """Integrate a list-of-tensors system from ta to tb (tb may be < ta) with torch ops under no_grad."""
   with torch.no_grad():
+    if method in ADAPTIVE_TABLEAUS:
+      # adaptive solvers ignore the fixed-grid keys the reference always passes (step_size, max_iters)
+      return integrate_system_adaptive(f, state, ta, tb, method, rtol, atol, first_step=options.get('first_step'))
     if method in FIXED_STEPS:
       h = float(options.get('step_size', abs(tb - ta)))
       n = max(1, int(torch.ceil(torch.tensor(abs(tb - ta) / h - 1e-9)).item()))
@@ -397,5 +504,5 @@ def _integrate_system(f, state, ta, tb, method, options, rtol, atol):
           state = [y + (a + 3 * (b + c) + e) * dt * 0.125 for y, a, b, c, e in zip(state, k1, k2, k3, k4)]
         cur = nxt
       return state
-    raise NotImplementedError('adjoint_method %r: fixed-grid adjoint solvers (euler, midpoint, rk4) are built; the '
-                              'adaptive ones are not yet' % method)
+    raise ValueError('Invalid adjoint method "{}". Must be one of {}'.format(
+      method, sorted(list(FIXED_STEPS) + list(ADAPTIVE_TABLEAUS))))

@@ -118,9 +118,9 @@ def training_blockers(opt):
     why.append('transformer backward is built for attention_type=scaled_dot, softmax, attention_norm_idx=0')
   if opt['function'] == 'transformer' and opt['hidden_dim'] % 4 != 0:
     why.append('transformer backward needs hidden_dim %% 4 == 0 (got %d)' % opt['hidden_dim'])
-  if opt.get('adjoint') and opt.get('adjoint_method') not in ('euler', 'midpoint', 'rk4'):
-    why.append('adjoint_method=%r: only the fixed-grid adjoint solvers (euler, midpoint, rk4) are built'
-               % opt.get('adjoint_method'))
+  if opt.get('adjoint') and opt.get('adjoint_method') not in ('euler', 'midpoint', 'rk4', 'dopri5', 'adaptive_heun',
+                                                              'bosh3'):
+    why.append('adjoint_method=%r: built are euler, midpoint, rk4, dopri5, adaptive_heun, bosh3' % opt.get('adjoint_method'))
   return why
 
 

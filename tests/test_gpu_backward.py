@@ -37,9 +37,10 @@ def _make(function, n, d, ad, heads, method='rk4', adjoint=False, seed=0, **extr
   edge_index = make_graph(n, 6 * n, max_degree=150, seed=seed)
   torch.manual_seed(seed + 1)
   x = torch.randn(n, d)
-  opt = default_opt(function=function, block='constant', hidden_dim=d, attention_dim=ad, heads=heads, method=method,
-                    step_size=0.5, time=1.0, add_source=True, adjoint=adjoint, adjoint_method='rk4',
-                    adjoint_step_size=0.5, **extra)
+  kw = dict(function=function, block='constant', hidden_dim=d, attention_dim=ad, heads=heads, method=method,
+            step_size=0.5, time=1.0, add_source=True, adjoint=adjoint, adjoint_method='rk4', adjoint_step_size=0.5)
+  kw.update(extra)
+  opt = default_opt(**kw)
   data = Data(x=x, edge_index=edge_index, edge_attr=None, num_nodes=n)
   cls = ODEFuncTransformerAtt if function == 'transformer' else LaplacianODEFunc
   block = ConstantODEblock(cls, (), opt, data, DEV, t=torch.tensor([0, opt['time']])).to(DEV)
@@ -223,3 +224,25 @@ def test_adjoint_gradients_close_to_direct_gradients():
     nfe_after_backward = block.odefunc.nfe
     assert nfe_after_backward > 8 or not adjoint      # the adjoint pass evaluates the function again (bm meter)
   assert_grads_close(grads[True], grads[False], 5e-2, ['x'] + NAMES['transformer'])
+
+
+@pytest.mark.parametrize('adjoint_method', ['adaptive_heun', 'dopri5'])
+def test_adaptive_adjoint_gradients_close_to_direct_gradients(adjoint_method):
+  """The reference's DEFAULT adjoint method is adaptive_heun (src/run_GNN.py:334; Computers uses dopri5): the augmented
+  system (y, a_y, a_theta) integrated backwards by the adaptive solver (autograd_rhs.integrate_system_adaptive, every
+  RHS evaluation and its VJP on the native kernels) vs backprop through a fine fixed-grid forward of the same block."""
+  n, d = 300, 32
+  grads = {}
+  for adjoint in (False, True):
+    block, opt, edge_index, x = _make('transformer', n, d, 16, 4, method='rk4', adjoint=adjoint, seed=6,
+                                      step_size=0.125, adjoint_method=adjoint_method, tol_scale_adjoint=1000.0)
+    xd = x.to(DEV).requires_grad_(True)
+    block.set_x0(x.to(DEV))
+    torch.manual_seed(3)
+    w = torch.randn(n, d).to(DEV)
+    z = block(xd)
+    (z * w).sum().backward()
+    grads[adjoint] = [xd.grad.clone()] + [dict(block.named_parameters())[k].grad.clone() for k in NAMES['transformer']]
+    for gr in grads[adjoint]:
+      assert torch.isfinite(gr).all()
+  assert_grads_close(grads[True], grads[False], 2e-2, ['x'] + NAMES['transformer'])
