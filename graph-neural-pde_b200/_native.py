@@ -15,7 +15,7 @@ GRAND_TILE = 32
 GRAND_SEG_EDGES = int(os.environ.get('GRAND_SEG_EDGES', '512'))   # rows longer than this are cut into segments
 GRAND_MAX_HEADS = 8
 GRAND_MAX_TERMS = 8
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 SCORE_TYPES = {'scaled_dot': 0, 'cosine_sim': 1, 'pearson': 2, 'exp_kernel': 3, 'exp_kernel2': 4, 'gat': 5}
 NORM_SOFTMAX, NORM_SQUAREPLUS = 0, 1
@@ -85,6 +85,8 @@ SIGNATURES = {
   'grand_launch_count': (C.c_int64, []),
   'grand_workspace_sizes': (C.c_int, [C.POINTER(GrandGraph), C.POINTER(GrandAttention)] + [C.POINTER(C.c_int64)] * 10),
   'grand_project_qk': (C.c_int, [_P, C.c_int32, C.c_int32, C.POINTER(GrandAttention), _P, _P, _P]),
+  'grand_linear': (C.c_int, [_P, C.c_int32, C.c_int32, _P, _P, C.c_int32, _P, C.c_int32, _P]),
+  'grand_set_projection_impl': (C.c_int, [C.c_int32]),
   'grand_rhs_attention': (C.c_int, [C.POINTER(GrandGraph), C.POINTER(GrandAttention), _P, C.POINTER(GrandWorkspace),
                                      C.POINTER(GrandEpilogue), _P]),
   'grand_rhs_attention_edges': (C.c_int, [C.POINTER(GrandGraph), C.POINTER(GrandAttention), _P,

@@ -10,7 +10,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(HERE, 'libgrand_b200.so')
-SOURCES = ['project.cu', 'project_mma.cu', 'rhs_window.cu', 'rhs_stream.cu', 'rhs_ring.cu', 'rhs_coop.cu', 'rhs_backward.cu', 'edge_kernels.cu', 'capi.cu', 'dopri5_device.cu',
+SOURCES = ['project.cu', 'project_mma.cu', 'project_tc.cu', 'linear.cu', 'rhs_window.cu', 'rhs_stream.cu', 'rhs_ring.cu', 'rhs_coop.cu', 'rhs_backward.cu', 'edge_kernels.cu', 'capi.cu', 'dopri5_device.cu',
            'plan_host.cu']
 HEADERS = ['common.cuh', 'attention.cuh', 'edge_common.cuh', 'rhs_stream.cu', os.path.join('..', '..', 'include', 'grand_b200.h')]
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',

@@ -24,6 +24,9 @@ int cuda_fail(cudaError_t e, const char* what) {
   return GRAND_ECUDA;
 }
 
+int launch_linear(const float* x, int rows, int d_in, const float* w, const float* b, int d_out, float* y, int ldy,
+                  cudaStream_t stream);
+void set_projection_impl(int impl);
 int launch_project_qk(const float* x, int n_rows, int n_cols, int d, const float* wq, const float* bq,
                       const float* wk, const float* bk, int ad, float* q, float* k, cudaStream_t stream);
 int rhs_attention_impl(const grand_graph* g, const grand_attention* a, const float* x, const grand_workspace* ws,
@@ -219,6 +222,19 @@ int grand_project_qk(const float* x, int32_t n_rows, int32_t n_cols, const grand
   GRAND_REQUIRE(n_rows >= 0 && n_cols >= n_rows && a->d > 0 && a->ad > 0, GRAND_EINVAL, "project_qk: bad sizes");
   const int ad_eff = a->score_type == GRAND_SCORE_EXP_KERNEL2 ? 2 * a->ad : a->ad;
   return launch_project_qk(x, n_rows, n_cols, a->d, a->wq, a->bq, a->wk, a->bk, ad_eff, q, k, (cudaStream_t)stream);
+}
+
+int grand_linear(const float* x, int32_t n_rows, int32_t d_in, const float* w, const float* b, int32_t d_out, float* y,
+                 int32_t ldy, void* stream) {
+  GRAND_REQUIRE(x && w && y, GRAND_EINVAL, "linear: null argument");
+  GRAND_REQUIRE(n_rows >= 0 && d_in > 0 && d_out > 0 && ldy >= d_out, GRAND_EINVAL, "linear: bad sizes");
+  return launch_linear(x, n_rows, d_in, w, b, d_out, y, ldy, (cudaStream_t)stream);
+}
+
+int grand_set_projection_impl(int32_t impl) {
+  GRAND_REQUIRE(impl >= 0 && impl <= 2, GRAND_EINVAL, "set_projection_impl: 0 (ffma), 1 (mma.sync) or 2 (tcgen05)");
+  set_projection_impl(impl);
+  return GRAND_OK;
 }
 
 int grand_rhs_attention(const grand_graph* g, const grand_attention* a, const float* x, const grand_workspace* ws,

@@ -12,6 +12,10 @@
 
 namespace grand {
 
+#ifndef GRAND_PROJ_DEFAULT
+#define GRAND_PROJ_DEFAULT 1   // until the tcgen05 kernel has been validated on a B200, then 2
+#endif
+
 constexpr int kProjThreads = 256;
 
 template <int RT, int OT>
@@ -139,20 +143,33 @@ project_qk_kernel(const float* __restrict__ x, int n_rows, int n_cols, int d, in
 int launch_project_qk_mma(const float* x, int n_rows, int n_cols, int d, const float* wq, const float* bq,
                           const float* wk, const float* bk, int ad, float* q, float* k, cudaStream_t stream);
 
-// GRAND_PROJ=ffma forces the fp32 FFMA kernel (A/B and fallback); default: 3xTF32 tensor-core kernel where it applies
-static bool use_mma() {
-  static int v = -1;
-  if (v < 0) {
+int launch_linear_tc(const float* x, int n_x_rows, int d, const float* w0, const float* b0, int n0, float* y0, int rows0,
+                     int ld0, const float* w1, const float* b1, int n1, float* y1, int rows1, int ld1,
+                     cudaStream_t stream);
+
+// Which kernel computes the projections: 2 = tcgen05 / TMEM / TMA (project_tc.cu), 1 = mma.sync 3xTF32 (project_mma.cu),
+// 0 = fp32 FFMA.  A kernel that does not cover a shape hands over to the next one.  GRAND_PROJ=tc|mma|ffma is read once;
+// grand_set_projection_impl overrides it at run time (in-process A/B measurements).
+static int g_proj_impl = -1;
+int projection_impl() {
+  if (g_proj_impl < 0) {
     const char* e = getenv("GRAND_PROJ");
-    v = (e != nullptr && !strcmp(e, "ffma")) ? 0 : 1;
+    g_proj_impl = (e != nullptr && !strcmp(e, "ffma")) ? 0 : (e != nullptr && !strcmp(e, "mma")) ? 1
+                : (e != nullptr && !strcmp(e, "tc")) ? 2 : GRAND_PROJ_DEFAULT;
   }
-  return v == 1;
+  return g_proj_impl;
 }
+void set_projection_impl(int impl) { g_proj_impl = impl; }
 
 int launch_project_qk(const float* x, int n_rows, int n_cols, int d, const float* wq, const float* bq,
                       const float* wk, const float* bk, int ad, float* q, float* k, cudaStream_t stream) {
   if (n_cols <= 0) return GRAND_OK;
-  if (use_mma()) {
+  const int impl = projection_impl();
+  if (impl >= 2) {
+    const int rc = launch_linear_tc(x, n_cols, d, wq, bq, ad, q, n_rows, ad, wk, bk, ad, k, n_cols, ad, stream);
+    if (rc != GRAND_EUNSUPPORTED) return rc;
+  }
+  if (impl >= 1) {
     const int rc = launch_project_qk_mma(x, n_rows, n_cols, d, wq, bq, wk, bk, ad, q, k, stream);
     if (rc != GRAND_EUNSUPPORTED) return rc;
   }

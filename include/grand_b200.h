@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define GRAND_ABI_VERSION 2
+#define GRAND_ABI_VERSION 3
 
 /* error codes */
 #define GRAND_OK 0
@@ -194,6 +194,18 @@ int grand_workspace_sizes(const grand_graph* g, const grand_attention* a, int64_
  * the mix_features=False path and is not computed). */
 int grand_project_qk(const float* x, int32_t n_rows, int32_t n_cols, const grand_attention* a, float* q, float* k,
                      void* stream);
+
+/* y = x w^T + b: the dense layers of the model shell around the ODE block -- encoder m1 (and m11 / m12 with use_mlp),
+ * decoder m2 (reference src/GNN.py:23-31, 60-71; src/base_classes.py:110-127).  x [n_rows, d_in], w [d_out, d_in]
+ * (nn.Linear layout), b [d_out] or null, y [n_rows, ldy].  d_in <= 128 (multiple of 4) with d_out a multiple of 4 runs on
+ * the tcgen05 / TMEM / TMA kernel of csrc/project_tc.cu (3xTF32, fp32-class accuracy), other shapes on an exact fp32
+ * tiled kernel. */
+int grand_linear(const float* x, int32_t n_rows, int32_t d_in, const float* w, const float* b, int32_t d_out, float* y,
+                 int32_t ldy, void* stream);
+
+/* Measurement switch (process-wide): which kernel computes the projections -- 2 tcgen05 (csrc/project_tc.cu), 1 mma.sync
+ * (csrc/project_mma.cu), 0 fp32 FFMA (csrc/project.cu).  A kernel that does not cover a shape hands over to the next. */
+int grand_set_projection_impl(int32_t impl);
 
 /* One GRAND-nl RHS evaluation: ODEFuncTransformerAtt.forward (reference :38-53) = projection, per-edge scores,
  * segment softmax / squareplus, head mean, (A (.) a) X aggregation, residual, RK stage combine.  Picks the fused
