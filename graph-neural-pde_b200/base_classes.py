@@ -10,6 +10,7 @@ from torch import nn
 
 from .engine import RhsEngine
 from .graph_plan import GraphPlan
+from .linear import NativeLinear
 from .utils import Meter
 
 
@@ -212,7 +213,7 @@ class BaseGNN(nn.Module):
     self.regularization_fns, self.regularization_coeffs = create_regularization_fns(self.opt)
 
   def _add_linear(self, name, n_in, n_out):
-    setattr(self, name, nn.Linear(n_in, n_out))
+    setattr(self, name, NativeLinear(n_in, n_out))   # nn.Linear state_dict keys; forward on the native library
 
   def getNFE(self):
     return self.odeblock.odefunc.nfe + self.odeblock.reg_odefunc.odefunc.nfe

@@ -204,7 +204,8 @@ int grand_linear(const float* x, int32_t n_rows, int32_t d_in, const float* w, c
                  int32_t ldy, void* stream);
 
 /* Measurement switch (process-wide): which kernel computes the projections -- 2 tcgen05 (csrc/project_tc.cu), 1 mma.sync
- * (csrc/project_mma.cu), 0 fp32 FFMA (csrc/project.cu).  A kernel that does not cover a shape hands over to the next. */
+ * (csrc/project_mma.cu), 0 fp32 FFMA (csrc/project.cu), -1 back to the default (or the GRAND_PROJ environment variable).
+ * A kernel that does not cover a shape hands over to the next. */
 int grand_set_projection_impl(int32_t impl);
 
 /* One GRAND-nl RHS evaluation: ODEFuncTransformerAtt.forward (reference :38-53) = projection, per-edge scores,

@@ -308,11 +308,18 @@ def test_native_row_packing_matches_python_rule():
     pack_short_rows(np.array([-1, 2]), 32, 8)
 
 
-def test_model_shell_matches_reference(golden):
+def test_model_shell_matches_reference(golden, monkeypatch):
   """Encoder / decoder either side of the ODE block (reference src/GNN.py:17-77, src/base_classes.py:98-131), eval
   mode, every shell option: `embed` must reproduce the tensor the reference hands to its block and `readout` the
-  reference's logits from the reference's block output (tests/golden/make_golden_v3.py recorded both)."""
+  reference's logits from the reference's block output (tests/golden/make_golden_v3.py recorded both).  This is the
+  shell's WIRING (dropout / MLP / concatenation / augmentation order) on the CPU: the dense layers themselves are the
+  native library's (linear.NativeLinear refuses CPU tensors; tests/test_gpu_models.py runs them on the GPU), so here
+  they are stood in for by the plain matmul."""
+  from graph_neural_pde_b200 import linear as L
   from graph_neural_pde_b200.models import GNN
+  with pytest.raises(Exception, match='CUDA-only'):
+    L.NativeLinear(3, 2)(torch.zeros(4, 3))
+  monkeypatch.setattr(L.NativeLinear, 'forward', lambda self, x: torch.nn.functional.linear(x, self.weight, self.bias))
   from graph_neural_pde_b200.utils import DummyDataset
   names = sorted(k for k, v in golden.items() if v['kind'] == 'model_shell')
   assert len(names) == 8

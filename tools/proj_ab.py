@@ -102,4 +102,4 @@ if __name__ == '__main__':
   linear(169343, 40, 128, bias=False)
   linear(2485, 1433, 80)
   linear(2485, 80, 7)
-  N.check(N.lib().grand_set_projection_impl(1))
+  N.check(N.lib().grand_set_projection_impl(-1))
