@@ -85,6 +85,12 @@ SIGNATURES = {
   'grand_launch_count': (C.c_int64, []),
   'grand_workspace_sizes': (C.c_int, [C.POINTER(GrandGraph), C.POINTER(GrandAttention)] + [C.POINTER(C.c_int64)] * 10),
   'grand_project_qk': (C.c_int, [_P, C.c_int32, C.c_int32, C.POINTER(GrandAttention), _P, _P, _P]),
+  'grand_plan_create': (C.c_int, [_P, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_void_p)]),
+  'grand_plan_describe': (C.c_int, [C.c_void_p, C.POINTER(GrandGraph), C.POINTER(C.c_int32), C.POINTER(C.c_int64),
+                                    C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+  'grand_plan_image': (C.c_void_p, [C.c_void_p]),
+  'grand_plan_bind': (C.c_int, [C.c_void_p, _P, C.POINTER(GrandGraph)]),
+  'grand_plan_destroy': (None, [C.c_void_p]),
   'grand_linear': (C.c_int, [_P, C.c_int32, C.c_int32, _P, _P, C.c_int32, _P, C.c_int32, _P]),
   'grand_set_projection_impl': (C.c_int, [C.c_int32]),
   'grand_rhs_attention': (C.c_int, [C.POINTER(GrandGraph), C.POINTER(GrandAttention), _P, C.POINTER(GrandWorkspace),

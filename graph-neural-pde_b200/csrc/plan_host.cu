@@ -1,5 +1,5 @@
-// Host-side part of the graph plan (no device code): the one step of graph_plan.py that is inherently sequential.
-// Everything else of the plan is data-parallel index arithmetic done with torch ops on the device.
+// The graph plan, built natively on the host (no device code): grand_plan_create and its helpers.  graph_plan.py
+// only wraps the resulting image in tensors.
 #include <stdint.h>
 
 #include "common.cuh"
@@ -30,5 +30,213 @@ int64_t grand_plan_pack_rows(const int64_t* deg, int64_t n_rows, int32_t tile, i
   if (rows) { first[w] = start; count[w] = rows; ++w; }
   return w;
 }
+
+// ---- the whole graph plan, natively (include/grand_b200.h: grand_plan_create) -----------------------------------------
+}  // extern "C"
+
+#include <algorithm>
+#include <new>
+#include <vector>
+
+struct grand_plan_host {
+  grand_graph counts;                       // scalar fields; pointer fields stay null (grand_plan_bind fills a copy)
+  int32_t max_degree, seg_edges;
+  int64_t off[GRAND_PLAN_ARRAYS], cnt[GRAND_PLAN_ARRAYS];
+  std::vector<int32_t> image;               // all arrays back to back, every start a multiple of 16 bytes
+};
+
+namespace {
+
+// rows [of the given list] ordered by degree, longest first, ties in row order (== torch.argsort(descending, stable))
+void sort_longest_first(std::vector<int32_t>& rows, const std::vector<int64_t>& deg) {
+  std::stable_sort(rows.begin(), rows.end(), [&](int32_t a, int32_t b) { return deg[a] > deg[b]; });
+}
+
+}  // namespace
+
+extern "C" {
+
+int grand_plan_create(const int64_t* edge_index, int64_t n_edges, int32_t n_rows, int32_t n_cols, int32_t tile,
+                      int32_t max_rows, int32_t seg_edges, grand_plan_host** out) {
+  using grand::set_error;
+  if (!out) return GRAND_EINVAL;
+  *out = nullptr;
+  GRAND_REQUIRE(n_edges >= 0 && n_rows >= 0 && n_cols >= 0 && (n_edges == 0 || edge_index), GRAND_EINVAL,
+                "plan_create: null edge list or negative sizes");
+  GRAND_REQUIRE(n_edges < ((int64_t)1 << 31) && tile == GRAND_TILE && max_rows > 0 && max_rows <= GRAND_MAX_PACKED_ROWS,
+                GRAND_EUNSUPPORTED, "plan_create: needs < 2^31 edges, tile == %d, max_rows <= %d", GRAND_TILE,
+                GRAND_MAX_PACKED_ROWS);
+  GRAND_REQUIRE(seg_edges >= tile && seg_edges % tile == 0, GRAND_EINVAL, "plan_create: seg_edges must be a multiple of the tile");
+  const int64_t* row = edge_index;
+  const int64_t* col = edge_index + n_edges;
+  const int64_t E = n_edges;
+  try {
+    // 1. CSR by edge_index[0], stable (edges of a row keep the caller's relative order): counting sort
+    std::vector<int64_t> deg(n_rows, 0), cdeg(n_cols, 0);
+    for (int64_t e = 0; e < E; ++e) {
+      GRAND_REQUIRE(row[e] >= 0 && row[e] < n_rows && col[e] >= 0 && col[e] < n_cols, GRAND_EINVAL,
+                    "plan_create: edge %lld = (%lld, %lld) out of range [%d, %d)", (long long)e, (long long)row[e],
+                    (long long)col[e], n_rows, n_cols);
+      ++deg[row[e]];
+      ++cdeg[col[e]];
+    }
+    std::vector<int32_t> rowptr(n_rows + 1, 0), colptr(n_cols + 1, 0);
+    for (int32_t r = 0; r < n_rows; ++r) rowptr[r + 1] = rowptr[r] + (int32_t)deg[r];
+    for (int32_t c = 0; c < n_cols; ++c) colptr[c + 1] = colptr[c] + (int32_t)cdeg[c];
+    std::vector<int32_t> col_csr(E), erow(E), eid(E), csc_pos(E);
+    {
+      std::vector<int32_t> cur(rowptr.begin(), rowptr.end() - 1);
+      for (int64_t e = 0; e < E; ++e) {
+        const int32_t p = cur[row[e]]++;
+        col_csr[p] = (int32_t)col[e];
+        erow[p] = (int32_t)row[e];
+        eid[p] = (int32_t)e;
+      }
+      // CSC view: CSR positions ordered by column, stable in CSR position
+      std::vector<int32_t> ccur(colptr.begin(), colptr.end() - 1);
+      for (int64_t p = 0; p < E; ++p) csc_pos[ccur[col_csr[p]]++] = (int32_t)p;
+    }
+    int64_t max_degree = 0;
+    for (int32_t r = 0; r < n_rows; ++r) max_degree = std::max(max_degree, deg[r]);
+
+    // 2. tiles: chunks of the rows with more than `tile` edges first (longest rows first), then the packed windows
+    std::vector<int32_t> split_rows;
+    for (int32_t r = 0; r < n_rows; ++r)
+      if (deg[r] > tile) split_rows.push_back(r);
+    sort_longest_first(split_rows, deg);
+    std::vector<int32_t> split_tile0(split_rows.size() + 1, 0);
+    for (size_t i = 0; i < split_rows.size(); ++i)
+      split_tile0[i + 1] = split_tile0[i] + (int32_t)((deg[split_rows[i]] + tile - 1) / tile);
+    const int32_t n_split_tiles = split_tile0.back();
+    std::vector<int64_t> pfirst(std::max<int32_t>(n_rows, 1)), pcount(std::max<int32_t>(n_rows, 1));
+    const int64_t n_pack = grand_plan_pack_rows(deg.data(), n_rows, tile, max_rows, pfirst.data(), pcount.data());
+    if (n_pack < 0) return (int)n_pack;
+    const int64_t n_tiles = (int64_t)n_split_tiles + n_pack;
+    GRAND_REQUIRE(n_tiles < ((int64_t)1 << 31) / (2 * tile), GRAND_EUNSUPPORTED, "plan_create: too many windows");
+    std::vector<int32_t> tile_row(n_tiles), tile_beg(n_tiles), tile_nrows(n_tiles), tile_split(n_tiles);
+    for (size_t i = 0; i < split_rows.size(); ++i) {
+      const int32_t r = split_rows[i];
+      for (int32_t t = split_tile0[i], k = 0; t < split_tile0[i + 1]; ++t, ++k) {
+        tile_row[t] = r; tile_beg[t] = rowptr[r] + k * tile; tile_nrows[t] = 1; tile_split[t] = (int32_t)i;
+      }
+    }
+    for (int64_t w = 0; w < n_pack; ++w) {
+      const int64_t t = n_split_tiles + w;
+      tile_row[t] = (int32_t)pfirst[w]; tile_beg[t] = rowptr[pfirst[w]]; tile_nrows[t] = (int32_t)pcount[w]; tile_split[t] = -1;
+    }
+    // 3. window header (int4) and per-lane record (int2), see csrc/edge_common.cuh
+    std::vector<int32_t> win_hdr(n_tiles * 4), win_rec(n_tiles * tile * 2);
+    for (int64_t t = 0; t < n_tiles; ++t) {
+      const int32_t r0 = tile_row[t], beg = tile_beg[t], nr = tile_nrows[t];
+      const bool is_split = tile_split[t] >= 0;
+      const int32_t end = is_split ? std::min(beg + tile, rowptr[r0 + 1]) : rowptr[r0 + nr];
+      const int32_t cnt = end - beg;
+      GRAND_REQUIRE(cnt >= 0 && cnt <= tile, GRAND_EINVAL, "plan_create: internal error, window of %d edges", cnt);
+      win_hdr[4 * t + 0] = r0; win_hdr[4 * t + 1] = beg; win_hdr[4 * t + 2] = nr | (cnt << 8); win_hdr[4 * t + 3] = tile_split[t];
+      for (int32_t lane = 0; lane < tile; ++lane) {
+        const bool valid = lane < cnt;
+        int32_t lane_col = 0, kk = 0, seg_lo = lane, seg_hi = lane, row_lo = 0, row_hi = 0;
+        if (valid) {
+          const int32_t p = beg + lane;
+          lane_col = col_csr[p];
+          if (is_split) {
+            seg_lo = 0; seg_hi = cnt;
+          } else {
+            kk = erow[p] - r0;
+            seg_lo = rowptr[r0 + kk] - beg; seg_hi = rowptr[r0 + kk + 1] - beg;
+          }
+        }
+        if (lane < nr && !is_split) {
+          const int32_t rr = std::min(r0 + lane, n_rows - 1);
+          row_lo = rowptr[rr] - beg; row_hi = rowptr[rr + 1] - beg;
+        }
+        const uint32_t packed = (uint32_t)kk | ((uint32_t)seg_lo << 8) | ((uint32_t)seg_hi << 14) |
+                                ((uint32_t)row_lo << 20) | ((uint32_t)row_hi << 26);
+        win_rec[(t * tile + lane) * 2 + 0] = lane_col;
+        win_rec[(t * tile + lane) * 2 + 1] = (int32_t)packed;
+      }
+    }
+    // 4. work list of the persistent edge kernel: long segments (longest row first), medium rows (longest first)
+    std::vector<int32_t> long_rows, med_rows;
+    for (int32_t r = 0; r < n_rows; ++r) {
+      if (deg[r] > seg_edges) long_rows.push_back(r);
+      else if (deg[r] > tile) med_rows.push_back(r);
+    }
+    sort_longest_first(long_rows, deg);
+    sort_longest_first(med_rows, deg);
+    std::vector<int32_t> lrow_slot0(long_rows.size() + 1, 0);
+    for (size_t i = 0; i < long_rows.size(); ++i)
+      lrow_slot0[i + 1] = lrow_slot0[i] + (int32_t)((deg[long_rows[i]] + seg_edges - 1) / seg_edges);
+    const int32_t n_lunits = lrow_slot0.back();
+    std::vector<int32_t> seg_desc(((size_t)n_lunits + med_rows.size()) * 4);
+    for (size_t i = 0; i < long_rows.size(); ++i) {
+      const int32_t r = long_rows[i];
+      for (int32_t u = lrow_slot0[i], k = 0; u < lrow_slot0[i + 1]; ++u, ++k) {
+        const int32_t b = rowptr[r] + k * seg_edges;
+        seg_desc[4 * u + 0] = r; seg_desc[4 * u + 1] = b; seg_desc[4 * u + 2] = std::min(seg_edges, rowptr[r + 1] - b);
+        seg_desc[4 * u + 3] = (int32_t)i;
+      }
+    }
+    for (size_t i = 0; i < med_rows.size(); ++i) {
+      const size_t u = (size_t)n_lunits + i;
+      const int32_t r = med_rows[i];
+      seg_desc[4 * u + 0] = r; seg_desc[4 * u + 1] = rowptr[r]; seg_desc[4 * u + 2] = (int32_t)deg[r]; seg_desc[4 * u + 3] = -1;
+    }
+
+    // 5. pack everything into one image
+    grand_plan_host* P = new (std::nothrow) grand_plan_host();
+    GRAND_REQUIRE(P != nullptr, GRAND_ECUDA, "plan_create: out of host memory");
+    const std::vector<int32_t>* arrays[GRAND_PLAN_ARRAYS] = {
+      &rowptr, &col_csr, &erow, &eid, &win_hdr, &win_rec, &split_tile0, &colptr, &csc_pos, &seg_desc, &lrow_slot0,
+      &long_rows, &tile_row, &tile_beg, &tile_nrows, &tile_split};
+    int64_t total = 0;
+    for (int i = 0; i < GRAND_PLAN_ARRAYS; ++i) {
+      P->off[i] = total;
+      P->cnt[i] = (int64_t)arrays[i]->size();
+      total += (P->cnt[i] + 3) & ~(int64_t)3;
+    }
+    P->image.assign((size_t)std::max<int64_t>(total, 4), 0);
+    for (int i = 0; i < GRAND_PLAN_ARRAYS; ++i)
+      std::copy(arrays[i]->begin(), arrays[i]->end(), P->image.begin() + P->off[i]);
+    grand_graph& g = P->counts;
+    g = grand_graph();
+    g.n_rows = n_rows; g.n_cols = n_cols; g.n_edges = (int32_t)E; g.n_tiles = (int32_t)n_tiles;
+    g.n_split_rows = (int32_t)split_rows.size(); g.n_split_tiles = n_split_tiles;
+    g.n_lunits = n_lunits; g.n_munits = (int32_t)med_rows.size(); g.n_lrows = (int32_t)long_rows.size();
+    P->max_degree = (int32_t)max_degree;
+    P->seg_edges = seg_edges;
+    *out = P;
+    return GRAND_OK;
+  } catch (const std::bad_alloc&) {
+    set_error("plan_create: out of host memory");
+    return GRAND_ECUDA;
+  }
+}
+
+int grand_plan_describe(const grand_plan_host* plan, grand_graph* counts, int32_t* max_degree, int64_t* image_elems,
+                        int64_t* offsets, int64_t* elems) {
+  if (!plan) return GRAND_EINVAL;
+  if (counts) *counts = plan->counts;
+  if (max_degree) *max_degree = plan->max_degree;
+  if (image_elems) *image_elems = (int64_t)plan->image.size();
+  for (int i = 0; i < GRAND_PLAN_ARRAYS; ++i) {
+    if (offsets) offsets[i] = plan->off[i];
+    if (elems) elems[i] = plan->cnt[i];
+  }
+  return GRAND_OK;
+}
+
+const int32_t* grand_plan_image(const grand_plan_host* plan) { return plan ? plan->image.data() : nullptr; }
+
+int grand_plan_bind(const grand_plan_host* plan, const int32_t* image, grand_graph* g) {
+  if (!plan || !image || !g) return GRAND_EINVAL;
+  *g = plan->counts;
+  const int32_t** slots[12] = {&g->rowptr, &g->col, &g->erow, &g->eid, &g->win_hdr, &g->win_rec, &g->split_tile0,
+                               &g->colptr, &g->csc_pos, &g->seg_desc, &g->lrow_slot0, &g->lrow_row};
+  for (int i = 0; i < 12; ++i) *slots[i] = image + plan->off[i];
+  return GRAND_OK;
+}
+
+void grand_plan_destroy(grand_plan_host* plan) { delete plan; }
 
 }  // extern "C"

@@ -9,21 +9,31 @@
     order, several whole rows to a window (<= max_rows).  Every row belongs to a tile, also rows without edges (their
     output is -alpha x + beta x0).
   * CSC view (colptr, csc_pos) for attention_norm_idx = 1.
+  * work list of the persistent edge kernel (long segments, medium rows, packed windows).
 
-Pure index plumbing in torch ops; works on CPU tensors too (host-logic tests), the kernels only ever see the
-device copy.
+The build itself is native: `grand_plan_create` (csrc/plan_host.cu, host code -- counting sorts and one pass per array)
+produces ONE int32 image; this module copies it to the device in one transfer and exposes the arrays as views.  An edge
+list that lives on the GPU (the hard-attention block re-selects its edges on the device every training forward,
+reference src/block_transformer_hard_attention.py:60-90) is brought to the host first.  tests/_plan_reference.py keeps
+the torch-ops restatement this replaced; tests/test_host_logic.py compares the two array by array.
 """
+import ctypes as C
+import os
+
 import numpy as np
 import torch
 
 from . import _native as N
 
+PLAN_ARRAYS = ('rowptr', 'col', 'erow', 'eid', 'win_hdr', 'win_rec', 'split_tile0', 'colptr', 'csc_pos', 'seg_desc',
+               'lrow_slot0', 'lrow_row', 'tile_row', 'tile_beg', 'tile_nrows', 'tile_split')   # enum grand_plan_array
+_SHAPES = {'win_hdr': (-1, 4), 'win_rec': (-1, N.GRAND_TILE, 2), 'seg_desc': (-1, 4)}
+
 
 def pack_short_rows(deg, tile, max_rows):
-  """Greedy packing of consecutive short rows into windows: -> (first row, row count) per window (int64 arrays).
-  The pass is sequential by nature and runs in the native library (grand_plan_pack_rows, csrc/plan_host.cu: plain host
-  code, so it also works on a machine without a GPU); rows with more than `tile` edges are skipped (they are chunked
-  separately) and close the current window, because a window covers a contiguous CSR range."""
+  """Greedy packing of consecutive short rows into windows: -> (first row, row count) per window (int64 arrays); the
+  sequential pass of the plan (grand_plan_pack_rows, csrc/plan_host.cu).  Rows with more than `tile` edges are skipped
+  (they are chunked separately) and close the current window, because a window covers a contiguous CSR range."""
   deg = np.ascontiguousarray(deg, dtype=np.int64)
   n = len(deg)
   first = np.empty(max(n, 1), dtype=np.int64)
@@ -34,128 +44,58 @@ def pack_short_rows(deg, tile, max_rows):
   return first[:w].copy(), count[:w].copy()
 
 
+def default_seg_edges(n_edges):
+  """Large graphs: a warp takes a whole row of up to 512 in-edges (fewer partial sums, no statistics pre-pass for them;
+  ogbn-arxiv, TMA-ring kernel: 64 -> 362, 128 -> 288, 256 -> 265, 512 -> 254, 1024 -> 257, 2048 -> 296 us per launch).
+  Small graphs (everything L2-resident, a handful of units per warp): the launch lasts as long as its longest unit, so
+  long rows are cut finer and spread over more warps (measured on B200: Photo 165 -> 115 us per evaluation, Cora
+  56 -> 46 with 64-edge segments; ogbn-arxiv 342 us with 256 against 376 us with 128, profiles/README.md)."""
+  return N.GRAND_SEG_EDGES if (n_edges >= (1 << 20) or 'GRAND_SEG_EDGES' in os.environ) else 64
+
+
 class GraphPlan:
   def __init__(self, edge_index, num_nodes, device=None, num_cols=None, tile=N.GRAND_TILE, max_rows=8,
                seg_edges=None):
     assert edge_index.dim() == 2 and edge_index.shape[0] == 2, 'edge_index must be [2, E]'
     device = torch.device(device) if device is not None else edge_index.device
-    ei = edge_index.to(device=device, dtype=torch.long)
     n_rows = int(num_nodes)
     n_cols = int(num_cols) if num_cols is not None else n_rows
-    e = ei.shape[1]
-    if e > 0:
-      assert int(ei[0].max()) < n_rows and int(ei[1].max()) < n_cols and int(ei.min()) >= 0, 'edge_index out of range'
+    ei = edge_index.detach().to(device='cpu', dtype=torch.long).contiguous()
+    e = int(ei.shape[1])
     assert e < 2 ** 31 and n_cols < 2 ** 31
-    row, col = ei[0], ei[1]
-    perm = torch.argsort(row, stable=True)
-    deg = torch.bincount(row, minlength=n_rows)
-    rowptr = torch.zeros(n_rows + 1, dtype=torch.long, device=device)
-    rowptr[1:] = torch.cumsum(deg, 0)
-
-    n_tiles_of_row = torch.clamp((deg + tile - 1) // tile, min=1)
-    split_rows = torch.nonzero(n_tiles_of_row > 1).flatten()
-    # longest rows first: their chunks are scheduled first and hide the tail
-    if split_rows.numel() > 0:
-      order = torch.argsort(deg[split_rows], descending=True, stable=True)
-      split_rows = split_rows[order]
-    nt_split = n_tiles_of_row[split_rows]
-    split_tile0 = torch.zeros(split_rows.numel() + 1, dtype=torch.long, device=device)
-    split_tile0[1:] = torch.cumsum(nt_split, 0)
-    n_split_tiles = int(split_tile0[-1])
-    split_index = torch.arange(split_rows.numel(), device=device)
-    st_split = torch.repeat_interleave(split_index, nt_split)                 # split-row index of each split tile
-    st_k = torch.arange(n_split_tiles, device=device) - split_tile0[:-1][st_split]
-    st_row = split_rows[st_split]
-    st_beg = rowptr[st_row] + st_k * tile
-    # short rows (<= tile edges, also empty ones): consecutive rows are packed greedily into windows of <= tile
-    # edges and <= max_rows rows; a long row ends the current window
-    pr0, pn = pack_short_rows(deg.cpu().numpy(), tile, max_rows)
-    pack_row = torch.from_numpy(pr0).to(device)
-    pack_nrows = torch.from_numpy(pn).to(device)
-    tile_row = torch.cat([st_row, pack_row])
-    tile_beg = torch.cat([st_beg, rowptr[pack_row]])
-    tile_nrows = torch.cat([torch.ones_like(st_row), pack_nrows])
-    tile_split = torch.cat([st_split, torch.full_like(pack_row, -1)])
-
-    col_csr = col[perm]
-    # window header (int4) and per-lane record (int2), see csrc/edge_common.cuh
-    n_t = int(tile_row.numel())
-    is_split = tile_split >= 0
-    t_end = torch.where(is_split, torch.minimum(tile_beg + tile, rowptr[tile_row + 1]), rowptr[tile_row + tile_nrows])
-    t_cnt = t_end - tile_beg
-    win_hdr = torch.stack([tile_row, tile_beg, tile_nrows | (t_cnt << 8), tile_split], dim=1)
-    lane = torch.arange(tile, device=device).unsqueeze(0)                       # [1, 32]
-    pos = tile_beg.unsqueeze(1) + lane                                         # CSR position of every lane
-    lane_valid = lane < t_cnt.unsqueeze(1)
-    pos_c = torch.where(lane_valid, pos, torch.zeros_like(pos)).clamp(max=max(e - 1, 0))
-    lane_col = torch.where(lane_valid, col_csr[pos_c] if e > 0 else torch.zeros_like(pos), torch.zeros_like(pos))
-    lane_row = (row[perm][pos_c] if e > 0 else torch.zeros_like(pos))
-    kk = torch.where(lane_valid & ~is_split.unsqueeze(1), lane_row - tile_row.unsqueeze(1), torch.zeros_like(pos))
-    # lane range of the lane's own row inside the window
-    own_row = tile_row.unsqueeze(1) + kk
-    seg_lo = torch.where(is_split.unsqueeze(1), torch.zeros_like(pos), rowptr[own_row] - tile_beg.unsqueeze(1))
-    seg_hi = torch.where(is_split.unsqueeze(1), t_cnt.unsqueeze(1).expand_as(pos), rowptr[own_row + 1] - tile_beg.unsqueeze(1))
-    seg_lo = torch.where(lane_valid, seg_lo, lane.expand_as(pos))
-    seg_hi = torch.where(lane_valid, seg_hi, lane.expand_as(pos))
-    # lane range of row number `lane` of the window (lane < nrows)
-    has_row = lane < tile_nrows.unsqueeze(1)
-    rrow = (tile_row.unsqueeze(1) + lane).clamp(max=max(n_rows - 1, 0))
-    row_lo = torch.where(has_row & ~is_split.unsqueeze(1), rowptr[rrow] - tile_beg.unsqueeze(1), torch.zeros_like(pos))
-    row_hi = torch.where(has_row & ~is_split.unsqueeze(1), rowptr[rrow + 1] - tile_beg.unsqueeze(1), torch.zeros_like(pos))
-    packed = kk | (seg_lo << 8) | (seg_hi << 14) | (row_lo << 20) | (row_hi << 26)
-    packed = torch.where(packed >= 2 ** 31, packed - 2 ** 32, packed)           # two's complement into int32
-    win_rec = torch.stack([lane_col, packed], dim=2)                            # [n_tiles, 32, 2]
-    assert n_t == 0 or (int(t_cnt.max()) <= tile and int(t_cnt.min()) >= 0)
-    perm_c = torch.argsort(col_csr, stable=True)
-    cdeg = torch.bincount(col, minlength=n_cols)
-    colptr = torch.zeros(n_cols + 1, dtype=torch.long, device=device)
-    colptr[1:] = torch.cumsum(cdeg, 0)
-
-    # ---- work list of the persistent edge kernel (csrc/rhs_stream.cu): rows with more than `tile` in-edges are either
-    #      "medium" (<= seg_edges: one warp takes the whole row) or "long" (cut into segments of seg_edges edges whose
-    #      partial sums are merged by the last segment to finish).  Longest first: the tail of the kernel is made of the
-    #      small packed windows.
     if seg_edges is None:
-      # Large graphs: a warp takes a whole row of up to 512 in-edges (fewer partial sums, no statistics pre-pass for them;
-      # ogbn-arxiv, TMA-ring kernel: 64 -> 362, 128 -> 288, 256 -> 265, 512 -> 254, 1024 -> 257, 2048 -> 296 us per launch).
-      # Small graphs (everything L2-resident, a handful of units per warp): the launch lasts as long as its longest unit,
-      # so long rows are cut finer and spread over more warps (measured on B200: Photo 165 -> 115 us per evaluation, Cora
-      # 56 -> 46 with 64-edge segments; ogbn-arxiv 342 us with 256 against 376 us with 128, profiles/README.md).
-      seg_edges = N.GRAND_SEG_EDGES if (e >= (1 << 20) or 'GRAND_SEG_EDGES' in __import__('os').environ) else 64
+      seg_edges = default_seg_edges(e)
     assert seg_edges >= tile and seg_edges % tile == 0
-    long_rows = torch.nonzero(deg > seg_edges).flatten()
-    long_rows = long_rows[torch.argsort(deg[long_rows], descending=True, stable=True)]
-    med_rows = torch.nonzero((deg > tile) & (deg <= seg_edges)).flatten()
-    med_rows = med_rows[torch.argsort(deg[med_rows], descending=True, stable=True)]
-    nseg = (deg[long_rows] + seg_edges - 1) // seg_edges
-    lrow_slot0 = torch.zeros(long_rows.numel() + 1, dtype=torch.long, device=device)
-    lrow_slot0[1:] = torch.cumsum(nseg, 0)
-    n_lunits = int(lrow_slot0[-1])
-    l_index = torch.repeat_interleave(torch.arange(long_rows.numel(), device=device), nseg)
-    l_k = torch.arange(n_lunits, device=device) - lrow_slot0[:-1][l_index]
-    l_row = long_rows[l_index]
-    l_beg = rowptr[l_row] + l_k * seg_edges
-    l_cnt = torch.minimum(torch.full_like(l_beg, seg_edges), rowptr[l_row + 1] - l_beg)
-    seg_desc = torch.cat([torch.stack([l_row, l_beg, l_cnt, l_index], dim=1),
-                          torch.stack([med_rows, rowptr[med_rows], deg[med_rows], torch.full_like(med_rows, -1)], dim=1)])
-
-    i32 = lambda t: t.to(torch.int32).contiguous()
+    lib = N.lib()
+    handle = C.c_void_p()
+    rc = lib.grand_plan_create(ei.data_ptr() if e > 0 else None, e, n_rows, n_cols, int(tile), int(max_rows),
+                               int(seg_edges), C.byref(handle))
+    if rc != 0:
+      msg = lib.grand_last_error().decode()
+      if 'out of range' in msg:
+        raise AssertionError('edge_index out of range: ' + msg)
+      N.check(rc)
+    try:
+      counts = N.GrandGraph()
+      max_degree, image_elems = C.c_int32(), C.c_int64()
+      offsets, elems = (C.c_int64 * len(PLAN_ARRAYS))(), (C.c_int64 * len(PLAN_ARRAYS))()
+      N.check(lib.grand_plan_describe(handle, C.byref(counts), C.byref(max_degree), C.byref(image_elems), offsets, elems))
+      host = np.ctypeslib.as_array(C.cast(lib.grand_plan_image(handle), C.POINTER(C.c_int32)),
+                                   shape=(int(image_elems.value),))
+      image = torch.from_numpy(host.copy())
+    finally:
+      lib.grand_plan_destroy(handle)
+    self.image = image.to(device)                  # ONE transfer; every array below is a view into it
+    for i, name in enumerate(PLAN_ARRAYS):
+      view = self.image[int(offsets[i]):int(offsets[i]) + int(elems[i])]
+      setattr(self, name, view.view(*_SHAPES[name]) if name in _SHAPES else view)
     self.device = device
     self.n_rows, self.n_cols, self.n_edges = n_rows, n_cols, e
-    self.n_tiles = int(tile_row.numel())
-    self.n_split_rows = int(split_rows.numel())
-    self.n_split_tiles = n_split_tiles
-    self.max_degree = int(deg.max()) if n_rows > 0 and e > 0 else 0
-    self.rowptr, self.col, self.erow, self.eid = i32(rowptr), i32(col_csr), i32(row[perm]), i32(perm)
-    self.tile_row, self.tile_beg, self.tile_split = i32(tile_row), i32(tile_beg), i32(tile_split)
-    self.tile_nrows = i32(tile_nrows)
-    self.win_hdr, self.win_rec = i32(win_hdr), i32(win_rec)
-    self.split_tile0 = i32(split_tile0)
-    self.colptr, self.csc_pos = i32(colptr), i32(perm_c)
+    self.n_tiles, self.n_split_rows, self.n_split_tiles = counts.n_tiles, counts.n_split_rows, counts.n_split_tiles
+    self.n_lunits, self.n_munits, self.n_lrows = counts.n_lunits, counts.n_munits, counts.n_lrows
+    self.max_degree = int(max_degree.value)
     self.seg_edges = int(seg_edges)
-    self.n_lunits, self.n_munits, self.n_lrows = n_lunits, int(med_rows.numel()), int(long_rows.numel())
-    self.seg_desc, self.lrow_slot0, self.lrow_row = i32(seg_desc), i32(lrow_slot0), i32(long_rows)
-    self.eid_long = perm  # CSR position -> caller position (int64, for torch-side permutations)
+    self.eid_long = self.eid.long()                # CSR position -> caller position (for torch-side permutations)
     self._struct = None
 
   def struct(self):

@@ -344,6 +344,32 @@ int grand_integrate_fixed_sharded(const grand_graph* g, const grand_attention* a
  * number of windows or a negative error code.  The reference has no counterpart (torch_sparse.spmm takes raw COO). */
 int64_t grand_plan_pack_rows(const int64_t* deg, int64_t n_rows, int32_t tile, int32_t max_rows, int64_t* first,
                              int64_t* count);
+
+/* ---- the graph plan, natively (csr_build / plan_create / plan_destroy) -------------------------
+ * HOST functions (plain CPU code, no CUDA call).  grand_plan_create re-lays the caller's COO edge list
+ * (edge_index [2, n_edges], int64, host memory; what the reference hands to torch_sparse.spmm / PyG softmax at
+ * src/function_transformer_attention.py:25-36, 190-213) into everything `grand_graph` points at: CSR by edge_index[0]
+ * (stable), windows of <= GRAND_TILE edges (chunks of long rows first, longest row first, then packed short rows), the
+ * per-lane records, the CSC view, and the work list of the persistent edge kernel.  The result is ONE int32 image;
+ * grand_plan_describe gives its length, the scalar counts and the offset / element count of each array in the order of
+ * enum grand_plan_array; the caller copies the image to the device and grand_plan_bind fills a grand_graph whose pointers
+ * point into that copy.  The hard-attention block rebuilds its plan through this on every training forward
+ * (reference src/block_transformer_hard_attention.py:60-90 re-selects the edges there). */
+enum grand_plan_array {
+  GRAND_PLAN_ROWPTR = 0, GRAND_PLAN_COL, GRAND_PLAN_EROW, GRAND_PLAN_EID, GRAND_PLAN_WIN_HDR, GRAND_PLAN_WIN_REC,
+  GRAND_PLAN_SPLIT_TILE0, GRAND_PLAN_COLPTR, GRAND_PLAN_CSC_POS, GRAND_PLAN_SEG_DESC, GRAND_PLAN_LROW_SLOT0,
+  GRAND_PLAN_LROW_ROW, GRAND_PLAN_TILE_ROW, GRAND_PLAN_TILE_BEG, GRAND_PLAN_TILE_NROWS, GRAND_PLAN_TILE_SPLIT,
+  GRAND_PLAN_ARRAYS
+};
+typedef struct grand_plan_host grand_plan_host;
+int grand_plan_create(const int64_t* edge_index, int64_t n_edges, int32_t n_rows, int32_t n_cols, int32_t tile,
+                      int32_t max_rows, int32_t seg_edges, grand_plan_host** out);
+/* any output pointer may be null; offsets / elems have GRAND_PLAN_ARRAYS entries (int32 elements) */
+int grand_plan_describe(const grand_plan_host* plan, grand_graph* counts, int32_t* max_degree, int64_t* image_elems,
+                        int64_t* offsets, int64_t* elems);
+const int32_t* grand_plan_image(const grand_plan_host* plan);
+int grand_plan_bind(const grand_plan_host* plan, const int32_t* image, grand_graph* g);
+void grand_plan_destroy(grand_plan_host* plan);
 #ifdef __cplusplus
 }
 #endif

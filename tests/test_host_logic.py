@@ -29,7 +29,7 @@ from oracle import grand_oracle as O
 
 def test_library_exports_every_declared_symbol():
   header = open(os.path.join(ROOT, 'include', 'grand_b200.h')).read()
-  declared = set(re.findall(r'^(?:int|int64_t|const char\*)\s+(grand_[a-z0-9_]+)\s*\(', header, flags=re.M))
+  declared = set(re.findall(r'^(?:int|int64_t|void|const char\*|const int32_t\*)\s+(grand_[a-z0-9_]+)\s*\(', header, flags=re.M))
   assert declared == set(N.SIGNATURES), declared ^ set(N.SIGNATURES)
   assert os.path.exists(N.LIB_PATH), 'build the library first: python graph-neural-pde_b200/build_native.py'
   handle = ctypes.CDLL(N.LIB_PATH)
@@ -390,3 +390,41 @@ def test_reference_best_params_overlay():
     got = mod.reference_best_params(parse(case['argv']))
     for key, want in case['opt'].items():
       assert got[key] == want, '%s: %s = %r, reference %r' % (case['argv'], key, got[key], want)
+
+
+@pytest.mark.parametrize('n,m,max_degree,n_cols,seg', [
+  (400, 1500, 200, None, 64), (900, 3000, 350, None, 32), (900, 3000, 350, None, 256), (50, 20, 8, None, 64),
+  (300, 2500, 290, 450, 64),      # a shard: columns index [own | halo] rows
+  (7, 0, 4, None, 64),            # no edges at all: every row still gets a window
+  (0, 0, 4, None, 64),
+])
+def test_native_plan_equals_the_torch_restatement(n, m, max_degree, n_cols, seg):
+  """grand_plan_create (csrc/plan_host.cu) against tests/_plan_reference.py (the torch index-op builder it replaced):
+  every array of the plan bit for bit -- CSR / eid, windows, per-lane records, CSC view, work list."""
+  from _plan_reference import TorchPlan
+  if m > 0:
+    ei = make_graph(n, m, max_degree=max_degree, seed=n + m)
+    if n_cols is not None:        # redirect a third of the columns into the halo range
+      g = torch.Generator().manual_seed(5)
+      halo = torch.randint(n, n_cols, (ei.shape[1],), generator=g)
+      ei = torch.stack([ei[0], torch.where(torch.rand(ei.shape[1], generator=g) < 0.33, halo, ei[1])])
+  else:
+    ei = torch.zeros(2, 0, dtype=torch.long)
+  got = GraphPlan(ei, n, device='cpu', num_cols=n_cols, seg_edges=seg)
+  want = TorchPlan(ei, n, device='cpu', num_cols=n_cols, seg_edges=seg)
+  for name in ('n_rows', 'n_cols', 'n_edges', 'n_tiles', 'n_split_rows', 'n_split_tiles', 'max_degree', 'seg_edges',
+               'n_lunits', 'n_munits', 'n_lrows'):
+    assert getattr(got, name) == getattr(want, name), name
+  for name in ('rowptr', 'col', 'erow', 'eid', 'tile_row', 'tile_beg', 'tile_split', 'tile_nrows', 'win_hdr', 'win_rec',
+               'split_tile0', 'colptr', 'csc_pos', 'seg_desc', 'lrow_slot0', 'lrow_row'):
+    a, b = getattr(got, name), getattr(want, name)
+    assert a.dtype == torch.int32 and tuple(a.shape) == tuple(b.shape), (name, a.shape, b.shape)
+    assert torch.equal(a, b), name
+  assert torch.equal(got.eid_long, want.eid_long)
+
+
+def test_native_plan_rejects_bad_edge_lists():
+  with pytest.raises(AssertionError, match='out of range'):
+    GraphPlan(torch.tensor([[0, 5], [1, 1]]), 3, device='cpu')
+  with pytest.raises(AssertionError, match='out of range'):
+    GraphPlan(torch.tensor([[0, 1], [1, -1]]), 3, device='cpu')
