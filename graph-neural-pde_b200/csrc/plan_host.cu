@@ -36,7 +36,14 @@ int64_t grand_plan_pack_rows(const int64_t* deg, int64_t n_rows, int32_t tile, i
 
 #include <algorithm>
 #include <new>
+#include <thread>
 #include <vector>
+#ifdef GRAND_PLAN_TIMING
+#include <chrono>
+#define GRAND_PLAN_TICK(what) { auto now = std::chrono::steady_clock::now(); fprintf(stderr, "plan %-10s %.1f ms\n", what, std::chrono::duration<double, std::milli>(now - tick).count()); tick = now; }
+#else
+#define GRAND_PLAN_TICK(what)
+#endif
 
 struct grand_plan_host {
   grand_graph counts;                       // scalar fields; pointer fields stay null (grand_plan_bind fills a copy)
@@ -50,6 +57,52 @@ namespace {
 // rows [of the given list] ordered by degree, longest first, ties in row order (== torch.argsort(descending, stable))
 void sort_longest_first(std::vector<int32_t>& rows, const std::vector<int64_t>& deg) {
   std::stable_sort(rows.begin(), rows.end(), [&](int32_t a, int32_t b) { return deg[a] > deg[b]; });
+}
+
+// [0, n) cut into contiguous chunks, one host thread each (the calling thread takes the first)
+inline int plan_threads(int64_t n) {
+  if (n < (1 << 16)) return 1;
+  const unsigned hw = std::thread::hardware_concurrency();
+  return (int)std::min<unsigned>(8u, hw == 0 ? 1u : hw);
+}
+template <class F>
+void parallel_for(int64_t n, F body) {
+  const int T = plan_threads(n);
+  if (T == 1) { body(0, n); return; }
+  std::vector<std::thread> pool;
+  for (int t = 1; t < T; ++t) pool.emplace_back([=]() { body(n * t / T, n * (t + 1) / T); });
+  body(0, n / T);
+  for (auto& th : pool) th.join();
+}
+
+// ptr[k] = first output position of key k, order[p] = input index at output position p; equal keys keep their input order
+template <class Key>
+void stable_counting_sort(int64_t n, int32_t n_keys, Key key, std::vector<int32_t>& ptr, std::vector<int32_t>& order) {
+  const int T = plan_threads(n);
+  std::vector<std::vector<int32_t>> hist(T, std::vector<int32_t>((size_t)n_keys + 1, 0));
+  auto chunk = [&](int t, int64_t& lo, int64_t& hi) { lo = n * t / T; hi = n * (t + 1) / T; };
+  {
+    std::vector<std::thread> pool;
+    auto count = [&](int t) { int64_t lo, hi; chunk(t, lo, hi); for (int64_t i = lo; i < hi; ++i) ++hist[t][key(i)]; };
+    for (int t = 1; t < T; ++t) pool.emplace_back(count, t);
+    count(0);
+    for (auto& th : pool) th.join();
+  }
+  ptr.assign((size_t)n_keys + 1, 0);
+  int32_t run = 0;
+  for (int32_t k = 0; k < n_keys; ++k) {       // hist[t][k] becomes thread t's first position for key k
+    ptr[k] = run;
+    for (int t = 0; t < T; ++t) { const int32_t c = hist[t][k]; hist[t][k] = run; run += c; }
+  }
+  ptr[n_keys] = run;
+  order.resize((size_t)n);
+  {
+    std::vector<std::thread> pool;
+    auto scatter = [&](int t) { int64_t lo, hi; chunk(t, lo, hi); for (int64_t i = lo; i < hi; ++i) order[hist[t][key(i)]++] = (int32_t)i; };
+    for (int t = 1; t < T; ++t) pool.emplace_back(scatter, t);
+    scatter(0);
+    for (auto& th : pool) th.join();
+  }
 }
 
 }  // namespace
@@ -71,31 +124,24 @@ int grand_plan_create(const int64_t* edge_index, int64_t n_edges, int32_t n_rows
   const int64_t* col = edge_index + n_edges;
   const int64_t E = n_edges;
   try {
-    // 1. CSR by edge_index[0], stable (edges of a row keep the caller's relative order): counting sort
-    std::vector<int64_t> deg(n_rows, 0), cdeg(n_cols, 0);
-    for (int64_t e = 0; e < E; ++e) {
+#ifdef GRAND_PLAN_TIMING
+    auto tick = std::chrono::steady_clock::now();
+#endif
+    // 1. CSR by edge_index[0], stable (edges of a row keep the caller's relative order), and the CSC view: two counting
+    //    sorts, each split over a few host threads (per-thread histograms over contiguous chunks of the input keep it stable)
+    for (int64_t e = 0; e < E; ++e)
       GRAND_REQUIRE(row[e] >= 0 && row[e] < n_rows && col[e] >= 0 && col[e] < n_cols, GRAND_EINVAL,
                     "plan_create: edge %lld = (%lld, %lld) out of range [%d, %d)", (long long)e, (long long)row[e],
                     (long long)col[e], n_rows, n_cols);
-      ++deg[row[e]];
-      ++cdeg[col[e]];
-    }
-    std::vector<int32_t> rowptr(n_rows + 1, 0), colptr(n_cols + 1, 0);
-    for (int32_t r = 0; r < n_rows; ++r) rowptr[r + 1] = rowptr[r] + (int32_t)deg[r];
-    for (int32_t c = 0; c < n_cols; ++c) colptr[c + 1] = colptr[c] + (int32_t)cdeg[c];
-    std::vector<int32_t> col_csr(E), erow(E), eid(E), csc_pos(E);
-    {
-      std::vector<int32_t> cur(rowptr.begin(), rowptr.end() - 1);
-      for (int64_t e = 0; e < E; ++e) {
-        const int32_t p = cur[row[e]]++;
-        col_csr[p] = (int32_t)col[e];
-        erow[p] = (int32_t)row[e];
-        eid[p] = (int32_t)e;
-      }
-      // CSC view: CSR positions ordered by column, stable in CSR position
-      std::vector<int32_t> ccur(colptr.begin(), colptr.end() - 1);
-      for (int64_t p = 0; p < E; ++p) csc_pos[ccur[col_csr[p]]++] = (int32_t)p;
-    }
+    std::vector<int32_t> rowptr, colptr, eid, csc_pos, col_csr(E), erow(E);
+    stable_counting_sort(E, n_rows, [&](int64_t e) { return (int32_t)row[e]; }, rowptr, eid);
+    parallel_for(E, [&](int64_t lo, int64_t hi) {
+      for (int64_t p = lo; p < hi; ++p) { col_csr[p] = (int32_t)col[eid[p]]; erow[p] = (int32_t)row[eid[p]]; }
+    });
+    stable_counting_sort(E, n_cols, [&](int64_t p) { return col_csr[p]; }, colptr, csc_pos);
+    std::vector<int64_t> deg(n_rows);
+    for (int32_t r = 0; r < n_rows; ++r) deg[r] = rowptr[r + 1] - rowptr[r];
+    GRAND_PLAN_TICK("csr+csc")
     int64_t max_degree = 0;
     for (int32_t r = 0; r < n_rows; ++r) max_degree = std::max(max_degree, deg[r]);
 
@@ -124,14 +170,15 @@ int grand_plan_create(const int64_t* edge_index, int64_t n_edges, int32_t n_rows
       const int64_t t = n_split_tiles + w;
       tile_row[t] = (int32_t)pfirst[w]; tile_beg[t] = rowptr[pfirst[w]]; tile_nrows[t] = (int32_t)pcount[w]; tile_split[t] = -1;
     }
+    GRAND_PLAN_TICK("tiles")
     // 3. window header (int4) and per-lane record (int2), see csrc/edge_common.cuh
     std::vector<int32_t> win_hdr(n_tiles * 4), win_rec(n_tiles * tile * 2);
-    for (int64_t t = 0; t < n_tiles; ++t) {
+    parallel_for(n_tiles, [&](int64_t t_lo, int64_t t_hi) {
+    for (int64_t t = t_lo; t < t_hi; ++t) {
       const int32_t r0 = tile_row[t], beg = tile_beg[t], nr = tile_nrows[t];
       const bool is_split = tile_split[t] >= 0;
       const int32_t end = is_split ? std::min(beg + tile, rowptr[r0 + 1]) : rowptr[r0 + nr];
       const int32_t cnt = end - beg;
-      GRAND_REQUIRE(cnt >= 0 && cnt <= tile, GRAND_EINVAL, "plan_create: internal error, window of %d edges", cnt);
       win_hdr[4 * t + 0] = r0; win_hdr[4 * t + 1] = beg; win_hdr[4 * t + 2] = nr | (cnt << 8); win_hdr[4 * t + 3] = tile_split[t];
       for (int32_t lane = 0; lane < tile; ++lane) {
         const bool valid = lane < cnt;
@@ -156,6 +203,8 @@ int grand_plan_create(const int64_t* edge_index, int64_t n_edges, int32_t n_rows
         win_rec[(t * tile + lane) * 2 + 1] = (int32_t)packed;
       }
     }
+    });
+    GRAND_PLAN_TICK("windows")
     // 4. work list of the persistent edge kernel: long segments (longest row first), medium rows (longest first)
     std::vector<int32_t> long_rows, med_rows;
     for (int32_t r = 0; r < n_rows; ++r) {
@@ -183,6 +232,7 @@ int grand_plan_create(const int64_t* edge_index, int64_t n_edges, int32_t n_rows
       seg_desc[4 * u + 0] = r; seg_desc[4 * u + 1] = rowptr[r]; seg_desc[4 * u + 2] = (int32_t)deg[r]; seg_desc[4 * u + 3] = -1;
     }
 
+    GRAND_PLAN_TICK("worklist")
     // 5. pack everything into one image
     grand_plan_host* P = new (std::nothrow) grand_plan_host();
     GRAND_REQUIRE(P != nullptr, GRAND_ECUDA, "plan_create: out of host memory");
@@ -195,14 +245,18 @@ int grand_plan_create(const int64_t* edge_index, int64_t n_edges, int32_t n_rows
       P->cnt[i] = (int64_t)arrays[i]->size();
       total += (P->cnt[i] + 3) & ~(int64_t)3;
     }
-    P->image.assign((size_t)std::max<int64_t>(total, 4), 0);
-    for (int i = 0; i < GRAND_PLAN_ARRAYS; ++i)
-      std::copy(arrays[i]->begin(), arrays[i]->end(), P->image.begin() + P->off[i]);
+    P->image.resize((size_t)std::max<int64_t>(total, 4));
+    for (int i = 0; i < GRAND_PLAN_ARRAYS; ++i) {
+      const int32_t* src = arrays[i]->data();
+      int32_t* dst = P->image.data() + P->off[i];
+      parallel_for(P->cnt[i], [=](int64_t lo, int64_t hi) { std::copy(src + lo, src + hi, dst + lo); });
+    }
     grand_graph& g = P->counts;
     g = grand_graph();
     g.n_rows = n_rows; g.n_cols = n_cols; g.n_edges = (int32_t)E; g.n_tiles = (int32_t)n_tiles;
     g.n_split_rows = (int32_t)split_rows.size(); g.n_split_tiles = n_split_tiles;
     g.n_lunits = n_lunits; g.n_munits = (int32_t)med_rows.size(); g.n_lrows = (int32_t)long_rows.size();
+    GRAND_PLAN_TICK("image")
     P->max_degree = (int32_t)max_degree;
     P->seg_edges = seg_edges;
     *out = P;

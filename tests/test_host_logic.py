@@ -395,6 +395,7 @@ def test_reference_best_params_overlay():
 @pytest.mark.parametrize('n,m,max_degree,n_cols,seg', [
   (400, 1500, 200, None, 64), (900, 3000, 350, None, 32), (900, 3000, 350, None, 256), (50, 20, 8, None, 64),
   (300, 2500, 290, 450, 64),      # a shard: columns index [own | halo] rows
+  (30000, 120000, 3000, None, 512),   # enough edges for the multi-threaded counting sorts (> 2^16)
   (7, 0, 4, None, 64),            # no edges at all: every row still gets a window
   (0, 0, 4, None, 64),
 ])
