@@ -76,6 +76,24 @@ __device__ __forceinline__ float4 ld_stream4(const float* p) {
   return r;
 }
 #endif
+// d{0,1} += a * b{0,1} as ONE packed instruction (sm_100 FFMA2: fma.rn.f32x2, each half an IEEE fma -- bit-identical to
+// two fmaf).  GRAND_FFMA2=0 builds the scalar form (A/B).
+#ifndef GRAND_FFMA2
+#define GRAND_FFMA2 1
+#endif
+__device__ __forceinline__ void fma2(float& d0, float& d1, float a, float b0, float b1) {
+#if GRAND_FFMA2
+  unsigned long long pa, pb, pc;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(pa) : "f"(a), "f"(a));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(pb) : "f"(b0), "f"(b1));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(pc) : "f"(d0), "f"(d1));
+  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(pc) : "l"(pa), "l"(pb));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(d0), "=f"(d1) : "l"(pc));
+#else
+  d0 = fmaf(a, b0, d0);
+  d1 = fmaf(a, b1, d1);
+#endif
+}
 __device__ __forceinline__ void st_stream4(float* p, float4 v) {
   asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z),
                "f"(v.w));

@@ -11,53 +11,56 @@ int launch_linear_tc(const float* x, int n_x_rows, int d, const float* w0, const
                      cudaStream_t stream);
 int projection_impl();
 
-constexpr int kLinBM = 64, kLinBN = 64, kLinBK = 16, kLinThreads = 256;
+constexpr int kLinThreads = 256;   // 16 x 16 threads, (BM / 16) x (BN / 16) outputs each
 
-// 64 x 64 output tile per block, 4 x 4 outputs per thread, fp32 FFMA, k-slabs of 16 staged through shared memory
-// (transposed, padded: conflict-free column reads).  Sums run over k in increasing order: deterministic.
+// BM x BN output tile per block, fp32 FFMA, k-slabs of BK staged through shared memory (transposed, padded: conflict-free
+// column reads; a warp's global loads cover whole 128-byte row segments).  Sums run over k in increasing order:
+// deterministic.  Small problems take 32 x 32 tiles so that the grid still covers the machine.
+template <int BM, int BN, int BK>
 __global__ void __launch_bounds__(kLinThreads)
 linear_ffma_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,
                    float* __restrict__ y, int rows, int d_in, int d_out, int ldy) {
-  __shared__ float xs[kLinBK][kLinBM + 4];
-  __shared__ float ws[kLinBK][kLinBN + 4];
+  constexpr int TM = BM / 16, TN = BN / 16;
+  __shared__ float xs[BK][BM + 4];
+  __shared__ float ws[BK][BN + 4];
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
-  const int row0 = blockIdx.x * kLinBM, col0 = blockIdx.y * kLinBN;
-  float acc[4][4];
+  const int row0 = blockIdx.x * BM, col0 = blockIdx.y * BN;
+  float acc[TM][TN];
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < TM; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-  for (int k0 = 0; k0 < d_in; k0 += kLinBK) {
-    for (int idx = tid; idx < kLinBM * kLinBK; idx += kLinThreads) {
-      const int r = idx / kLinBK, k = idx - r * kLinBK;
+    for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+  for (int k0 = 0; k0 < d_in; k0 += BK) {
+    for (int idx = tid; idx < BM * BK; idx += kLinThreads) {
+      const int r = idx / BK, k = idx - r * BK;
       xs[k][r] = (row0 + r < rows && k0 + k < d_in) ? __ldg(x + (size_t)(row0 + r) * d_in + k0 + k) : 0.f;
     }
-    for (int idx = tid; idx < kLinBN * kLinBK; idx += kLinThreads) {
-      const int c = idx / kLinBK, k = idx - c * kLinBK;
+    for (int idx = tid; idx < BN * BK; idx += kLinThreads) {
+      const int c = idx / BK, k = idx - c * BK;
       ws[k][c] = (col0 + c < d_out && k0 + k < d_in) ? __ldg(w + (size_t)(col0 + c) * d_in + k0 + k) : 0.f;
     }
     __syncthreads();
+#pragma unroll 8
+    for (int k = 0; k < BK; ++k) {
+      float xv[TM], wv[TN];
 #pragma unroll
-    for (int k = 0; k < kLinBK; ++k) {
-      float xv[4], wv[4];
+      for (int i = 0; i < TM; ++i) xv[i] = xs[k][ty * TM + i];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) xv[i] = xs[k][ty * 4 + i];
+      for (int j = 0; j < TN; ++j) wv[j] = ws[k][tx * TN + j];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) wv[j] = ws[k][tx * 4 + j];
+      for (int i = 0; i < TM; ++i)
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(xv[i], wv[j], acc[i][j]);
+        for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(xv[i], wv[j], acc[i][j]);
     }
     __syncthreads();
   }
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int r = row0 + ty * 4 + i;
+  for (int i = 0; i < TM; ++i) {
+    const int r = row0 + ty * TM + i;
     if (r >= rows) continue;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int c = col0 + tx * 4 + j;
+    for (int j = 0; j < TN; ++j) {
+      const int c = col0 + tx * TN + j;
       if (c < d_out) y[(size_t)r * ldy + c] = acc[i][j] + (b != nullptr ? __ldg(b + c) : 0.f);
     }
   }
@@ -72,8 +75,14 @@ int launch_linear(const float* x, int rows, int d_in, const float* w, const floa
     const int rc = launch_linear_tc(x, rows, d_in, w, b, d_out, y, rows, ldy, nullptr, nullptr, pad, nullptr, 0, 4, stream);
     if (rc != GRAND_EUNSUPPORTED) return rc;
   }
-  dim3 grid((rows + kLinBM - 1) / kLinBM, (d_out + kLinBN - 1) / kLinBN);
-  linear_ffma_kernel<<<grid, kLinThreads, 0, stream>>>(x, w, b, y, rows, d_in, d_out, ldy);
+  const long blocks64 = (long)((rows + 63) / 64) * ((d_out + 63) / 64);
+  if (blocks64 >= 2 * num_sms()) {
+    dim3 grid((rows + 63) / 64, (d_out + 63) / 64);
+    linear_ffma_kernel<64, 64, 32><<<grid, kLinThreads, 0, stream>>>(x, w, b, y, rows, d_in, d_out, ldy);
+  } else {
+    dim3 grid((rows + 31) / 32, (d_out + 31) / 32);
+    linear_ffma_kernel<32, 32, 32><<<grid, kLinThreads, 0, stream>>>(x, w, b, y, rows, d_in, d_out, ldy);
+  }
   GRAND_CUDA_OK(cudaGetLastError());
   count_launch();
   return GRAND_OK;

@@ -13,7 +13,7 @@
 namespace grand {
 
 #ifndef GRAND_PROJ_DEFAULT
-#define GRAND_PROJ_DEFAULT 1   // until the tcgen05 kernel has been validated on a B200, then 2
+#define GRAND_PROJ_DEFAULT 2   // tcgen05 kernel (validated on B200: profiles/r02u_proj_ab.txt); shapes it does not cover fall through
 #endif
 
 constexpr int kProjThreads = 256;

@@ -46,6 +46,7 @@ struct TcArgs {
   int ld0, ld1;        // leading dimensions of Y0 / Y1 (floats)
   int n_tiles, stages;
   int tmem_cols, acc_stride;
+  int prefetch_tiles;  // tiles ahead of the ring that the producer requests into L2 (0 = off)
   const float* w0; const float* b0;
   const float* w1; const float* b1;
   float* y0; float* y1;
@@ -76,6 +77,11 @@ __device__ __forceinline__ void tc_fence_async_smem() { asm volatile("fence.prox
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
+__device__ __forceinline__ void tc_tma_prefetch_2d(const CUtensorMap* map, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];" ::"l"(reinterpret_cast<uint64_t>(map)), "r"(c0),
+               "r"(c1)
+               : "memory");
+}
 __device__ __forceinline__ void tc_tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
@@ -193,7 +199,16 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
     if (lane == 0) {
       int s = 0;
       uint32_t ph = 0;
+      // The ring holds ~1.25 tiles, less than the bandwidth-delay product of an HBM stream at one CTA per SM: tiles further
+      // ahead are requested into L2 (no shared memory needed), so that the ring's own loads see L2 latency
+      for (int a = 1; a <= A.prefetch_tiles; ++a)
+        for (int c = 0; c < A.nkc; ++c)
+          if (first_tile + (a - 1) * tile_step < A.n_tiles)
+            tc_tma_prefetch_2d(&xmap, c * kTcChunkCols, (first_tile + (a - 1) * tile_step) * kTcRows);
       for (int tile = first_tile; tile < A.n_tiles; tile += tile_step) {
+        const int ahead = tile + A.prefetch_tiles * tile_step;
+        if (A.prefetch_tiles > 0 && ahead < A.n_tiles)
+          for (int c = 0; c < A.nkc; ++c) tc_tma_prefetch_2d(&xmap, c * kTcChunkCols, ahead * kTcRows);
         for (int c = 0; c < A.nkc; ++c) {
           tc_mbar_wait(tc_smem_u32(empty + s), ph ^ 1u);          // first pass over the ring: passes immediately
           tc_mbar_expect_tx(tc_smem_u32(full + s), kTcTileBytes);
@@ -358,6 +373,15 @@ int launch_linear_tc(const float* x, int n_x_rows, int d, const float* w0, const
   int stages = (int)((budget - w_bytes - tail) / kTcStageBytes);
   if (stages > kTcMaxStages) stages = kTcMaxStages;
   A.stages = stages;
+  {
+    static int pf = -1;                  // GRAND_TC_PREFETCH=<tiles>: measurement switch, read once
+    if (pf < 0) {
+      const char* e = getenv("GRAND_TC_PREFETCH");
+      pf = e != nullptr ? atoi(e) : 2;
+      if (pf < 0 || pf > 8) pf = 2;
+    }
+    A.prefetch_tiles = pf;
+  }
   const size_t smem = w_bytes + (size_t)stages * kTcStageBytes + tail;
 
   CUtensorMap xmap;

@@ -76,8 +76,8 @@ struct RingState {
       const float a = __shfl_sync(kFull, ab, e);
       if (FULL || lane < q) {
         const float4 v = s[e * q];
-        acc[0] = fmaf(a, v.x, acc[0]); acc[1] = fmaf(a, v.y, acc[1]);
-        acc[2] = fmaf(a, v.z, acc[2]); acc[3] = fmaf(a, v.w, acc[3]);
+        fma2(acc[0], acc[1], a, v.x, v.y);
+        fma2(acc[2], acc[3], a, v.z, v.w);
       }
     }
   }

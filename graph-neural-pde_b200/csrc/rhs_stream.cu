@@ -28,6 +28,9 @@
 
 namespace grand {
 
+#ifndef GRAND_EPI_COEF_ONCE
+#define GRAND_EPI_COEF_ONCE 0   // measurement switch (tools/build_variants.sh)
+#endif
 #ifndef GRAND_STREAM_THREADS
 #define GRAND_STREAM_THREADS 320
 #endif
@@ -195,7 +198,7 @@ __device__ __forceinline__ void epi_load(const RhsArgs& A, unsigned rowoff, int 
 }
 
 #define GRAND_FMA4(y, c, v) \
-  { y.x = fmaf(c, v.x, y.x); y.y = fmaf(c, v.y, y.y); y.z = fmaf(c, v.z, y.z); y.w = fmaf(c, v.w, y.w); }
+  { fma2(y.x, y.y, c, v.x, v.y); fma2(y.z, y.w, c, v.z, v.w); }
 
 // residual + RK stage combine (same arithmetic, in the same order, as finish_row of rhs_window.cu)
 template <bool FULL, int R>
@@ -215,12 +218,28 @@ __device__ __forceinline__ void epi_finish(const RhsArgs& A, unsigned rowoff, in
     }
     if (A.ep.f_out != nullptr) st_stream4_hint(A.ep.f_out + o, f, pol_stream);
     if (A.ep.y_out != nullptr) {
+#if GRAND_EPI_COEF_ONCE
+      // ONE test of "coefficients on the device?" per row instead of one per coefficient
+      float cf, c0, c1, c2, c3;
+      if (A.ep.coef_dev != nullptr) {
+        cf = __ldg(A.ep.coef_dev); c0 = __ldg(A.ep.coef_dev + 1); c1 = __ldg(A.ep.coef_dev + 2);
+        c2 = __ldg(A.ep.coef_dev + 3); c3 = __ldg(A.ep.coef_dev + 4);
+      } else {
+        cf = A.ep.coef_f; c0 = A.ep.coef[0]; c1 = A.ep.coef[1]; c2 = A.ep.coef[2]; c3 = A.ep.coef[3];
+      }
+      float4 y = make_float4(cf * f.x, cf * f.y, cf * f.z, cf * f.w);
+      if (nt > 0) GRAND_FMA4(y, c0, E.t0[r]);
+      if (nt > 1) GRAND_FMA4(y, c1, E.t1[r]);
+      if (nt > 2) GRAND_FMA4(y, c2, E.t2[r]);
+      if (nt > 3) GRAND_FMA4(y, c3, E.t3[r]);
+#else
       const float cf = epi_coef_f(A.ep);
       float4 y = make_float4(cf * f.x, cf * f.y, cf * f.z, cf * f.w);
       if (nt > 0) GRAND_FMA4(y, epi_coef(A.ep, 0), E.t0[r]);
       if (nt > 1) GRAND_FMA4(y, epi_coef(A.ep, 1), E.t1[r]);
       if (nt > 2) GRAND_FMA4(y, epi_coef(A.ep, 2), E.t2[r]);
       if (nt > 3) GRAND_FMA4(y, epi_coef(A.ep, 3), E.t3[r]);
+#endif
       for (int t = 4; t < nt; ++t) {                               // dopri5 stages have up to 7 terms
         const float ct = epi_coef(A.ep, t);
         const float4 v = ld_stream4_hint(A.ep.term[t] + o, pol_stream);
@@ -266,8 +285,8 @@ __device__ __forceinline__ void gather_n(const float* __restrict__ xl, int d, in
   for (int u = 0; u < N; ++u)
 #pragma unroll
     for (int r = 0; r < R; ++r) {
-      acc[r][0] = fmaf(aa[u], xv[u][r].x, acc[r][0]); acc[r][1] = fmaf(aa[u], xv[u][r].y, acc[r][1]);
-      acc[r][2] = fmaf(aa[u], xv[u][r].z, acc[r][2]); acc[r][3] = fmaf(aa[u], xv[u][r].w, acc[r][3]);
+      fma2(acc[r][0], acc[r][1], aa[u], xv[u][r].x, xv[u][r].y);
+      fma2(acc[r][2], acc[r][3], aa[u], xv[u][r].z, xv[u][r].w);
     }
 }
 
