@@ -326,13 +326,13 @@ def algorithmic_bytes_l(n, e, d, add_source):
   return 4 * (2 * n * d + (n * d if add_source else 0)) + 8 * e + 4 * (n + 1)
 
 
-def edge_kernel_name(attention, d):
+def edge_kernel_name(attention, d, n_edges=1 << 20):
   """Which edge kernel the library launches for this workload (csrc/rhs_ring.cu ring_kernel_ok, csrc/rhs_stream.cu)."""
   sel = os.environ.get('GRAND_EDGE', '')
   ring_ok = d <= 128 and d % 4 == 0
   if sel == 'window':
     base = 'rhs_window_kernel'
-  elif ring_ok and sel != 'stream' and (attention or sel == 'ring'):
+  elif ring_ok and sel != 'stream' and ((attention and n_edges >= (1 << 20)) or sel == 'ring'):
     base = 'rhs_ring_kernel (neighbour rows staged through shared memory by cp.async.bulk)'
   else:
     base = 'rhs_stream_kernel'
@@ -662,7 +662,7 @@ def run_native_single(args):
     'gpu_launches_per_step': res['launches_per_step'],
     'clocks': res['clocks'],
     'roofline': {'bound': 'hbm',
-                 'kernel': edge_kernel_name(bool(ad), d),
+                 'kernel': edge_kernel_name(bool(ad), d, e),
                  'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
                  'traffic': dominant_traffic(name), 'peak_source': peak_src,
                  'algorithmic_bytes_per_launch': edge_bytes,

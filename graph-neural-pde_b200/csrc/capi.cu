@@ -232,8 +232,9 @@ int grand_linear(const float* x, int32_t n_rows, int32_t d_in, const float* w, c
 }
 
 int grand_set_projection_impl(int32_t impl) {
-  GRAND_REQUIRE(impl >= -1 && impl <= 2, GRAND_EINVAL,
-                "set_projection_impl: 0 (ffma), 1 (mma.sync), 2 (tcgen05) or -1 (back to the default / GRAND_PROJ)");
+  GRAND_REQUIRE(impl >= -1 && impl <= 3, GRAND_EINVAL,
+                "set_projection_impl: 0 (ffma), 1 (mma.sync), 2 (tcgen05, operands in shared memory), 3 (tcgen05, X in tensor "
+                "memory) or -1 (back to the default / GRAND_PROJ)");
   set_projection_impl(impl);
   return GRAND_OK;
 }

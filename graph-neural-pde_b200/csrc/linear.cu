@@ -8,7 +8,7 @@ namespace grand {
 
 int launch_linear_tc(const float* x, int n_x_rows, int d, const float* w0, const float* b0, int n0, float* y0, int rows0,
                      int ld0, const float* w1, const float* b1, int n1, float* y1, int rows1, int ld1,
-                     cudaStream_t stream);
+                     cudaStream_t stream, int variant);
 int projection_impl();
 
 constexpr int kLinThreads = 256;   // 16 x 16 threads, (BM / 16) x (BN / 16) outputs each
@@ -72,7 +72,8 @@ int launch_linear(const float* x, int rows, int d_in, const float* w, const floa
   if (projection_impl() >= 2 && (d_out & 3) == 0) {
     // outputs are padded to the next multiple of 16 with zero weight rows that are never stored
     const int pad = (16 - (d_out & 15)) & 15;
-    const int rc = launch_linear_tc(x, rows, d_in, w, b, d_out, y, rows, ldy, nullptr, nullptr, pad, nullptr, 0, 4, stream);
+    const int rc = launch_linear_tc(x, rows, d_in, w, b, d_out, y, rows, ldy, nullptr, nullptr, pad, nullptr, 0, 4, stream,
+                                    projection_impl());
     if (rc != GRAND_EUNSUPPORTED) return rc;
   }
   const long blocks64 = (long)((rows + 63) / 64) * ((d_out + 63) / 64);

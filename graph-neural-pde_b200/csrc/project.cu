@@ -145,7 +145,7 @@ int launch_project_qk_mma(const float* x, int n_rows, int n_cols, int d, const f
 
 int launch_linear_tc(const float* x, int n_x_rows, int d, const float* w0, const float* b0, int n0, float* y0, int rows0,
                      int ld0, const float* w1, const float* b1, int n1, float* y1, int rows1, int ld1,
-                     cudaStream_t stream);
+                     cudaStream_t stream, int variant);
 
 // Which kernel computes the projections: 2 = tcgen05 / TMEM / TMA (project_tc.cu), 1 = mma.sync 3xTF32 (project_mma.cu),
 // 0 = fp32 FFMA.  A kernel that does not cover a shape hands over to the next one.  GRAND_PROJ=tc|mma|ffma is read once;
@@ -155,7 +155,7 @@ int projection_impl() {
   if (g_proj_impl < 0) {
     const char* e = getenv("GRAND_PROJ");
     g_proj_impl = (e != nullptr && !strcmp(e, "ffma")) ? 0 : (e != nullptr && !strcmp(e, "mma")) ? 1
-                : (e != nullptr && !strcmp(e, "tc")) ? 2 : GRAND_PROJ_DEFAULT;
+                : (e != nullptr && !strcmp(e, "tc")) ? 2 : (e != nullptr && !strcmp(e, "tm")) ? 3 : GRAND_PROJ_DEFAULT;
   }
   return g_proj_impl;
 }
@@ -166,7 +166,7 @@ int launch_project_qk(const float* x, int n_rows, int n_cols, int d, const float
   if (n_cols <= 0) return GRAND_OK;
   const int impl = projection_impl();
   if (impl >= 2) {
-    const int rc = launch_linear_tc(x, n_cols, d, wq, bq, ad, q, n_rows, ad, wk, bk, ad, k, n_cols, ad, stream);
+    const int rc = launch_linear_tc(x, n_cols, d, wq, bq, ad, q, n_rows, ad, wk, bk, ad, k, n_cols, ad, stream, impl);
     if (rc != GRAND_EUNSUPPORTED) return rc;
   }
   if (impl >= 1) {

@@ -100,6 +100,25 @@ __device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t adesc, uin
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// A operand from TENSOR MEMORY (lane = row, one 32-bit column per k), B from shared memory
+__device__ __forceinline__ void tc_mma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n}\n" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// 32 consecutive columns of this thread's TMEM lane <- 32 registers
+__device__ __forceinline__ void tc_tmem_st32(uint32_t taddr, const uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,"
+      "%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};" ::"r"(taddr),
+      "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]),
+      "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]), "r"(v[20]),
+      "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]),
+      "r"(v[31])
+      : "memory");
+}
+__device__ __forceinline__ void tc_tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -322,6 +341,218 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
   }
 }
 
+// ---- variant 2: the split X chunks live in TENSOR MEMORY, shared memory only holds what TMA lands ---------------------------
+// The shared-memory version above moves every X byte through shared memory five times (TMA write, converter read, two
+// converter writes, ~three tensor-core reads): ~0.5 MB per 128-row tile, which is what bounds it (36 us on ogbn-arxiv,
+// no faster than mma.sync).  Here a converter thread owns ONE row of the tile (= one TMEM lane): it reads its 128 bytes
+// of the landed chunk (8 LDS.128, conflict-free under the 128-byte swizzle), splits them and stores hi / lo straight
+// into tensor memory (tcgen05.st 32x32b.x32), from where tcgen05.mma takes its A operand.  The landing buffer is free
+// as soon as it has been read, so shared memory holds 10 x 16 KB of loads in flight instead of 5 stages; the tensor
+// cores read only W from shared memory.
+//   TMEM columns: [0, 2 acc_stride) two accumulators, then a_stages x (32 hi | 32 lo).
+constexpr int kTmMaxRaw = 12;
+constexpr int kTmMaxA = 6;
+
+struct TmArgs {
+  TcArgs t;
+  int raw_slots, a_stages, a_col0;
+};
+
+__global__ void __launch_bounds__(kTcThreads, 1)
+linear_tm_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ TmArgs P) {
+  extern __shared__ __align__(1024) unsigned char tc_smem[];
+  const TcArgs& A = P.t;
+  unsigned char* base = tc_smem + ((1024u - (tc_smem_u32(tc_smem) & 1023u)) & 1023u);
+  const int N = A.n0 + A.n1;
+  const int w_chunk_bytes = N * 128;
+  unsigned char* w_hi = base;
+  unsigned char* w_lo = w_hi + (size_t)A.nkc * w_chunk_bytes;
+  unsigned char* raw0 = w_lo + (size_t)A.nkc * w_chunk_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(raw0 + (size_t)P.raw_slots * kTcTileBytes);
+  uint64_t* full = bars;                          // [raw_slots] TMA landed
+  uint64_t* raw_free = full + kTmMaxRaw;          // [raw_slots] the 128 converter threads have read the slot
+  uint64_t* a_ready = raw_free + kTmMaxRaw;       // [a_stages]  hi / lo of a chunk are in tensor memory (128 arrivals)
+  uint64_t* a_free = a_ready + kTmMaxA;           // [a_stages]  the MMAs reading the stage retired (tcgen05.commit)
+  uint64_t* acc_full = a_free + kTmMaxA;          // [2]
+  uint64_t* acc_empty = acc_full + 2;             // [2]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  float* bias = reinterpret_cast<float*>(tmem_ptr + 4);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
+    for (int s = 0; s < P.raw_slots; ++s) {
+      tc_mbar_init(tc_smem_u32(full + s), 1);
+      tc_mbar_init(tc_smem_u32(raw_free + s), kTcConvThreads);
+    }
+    for (int s = 0; s < P.a_stages; ++s) {
+      tc_mbar_init(tc_smem_u32(a_ready + s), kTcConvThreads);
+      tc_mbar_init(tc_smem_u32(a_free + s), 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      tc_mbar_init(tc_smem_u32(acc_full + b), 1);
+      tc_mbar_init(tc_smem_u32(acc_empty + b), kTcConvThreads);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc_smem_u32(tmem_ptr)),
+                 "r"((uint32_t)A.tmem_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  for (int o = tid; o < N; o += kTcThreads) {
+    const float* b = o < A.n0 ? A.b0 : A.b1;
+    bias[o] = b != nullptr ? __ldg(b + (o < A.n0 ? o : o - A.n0)) : 0.f;
+  }
+  {
+    const int c4_per_row = A.nkc * 8;
+    for (int idx = tid; idx < N * c4_per_row; idx += kTcThreads) {
+      const int n = idx / c4_per_row, p = idx - n * c4_per_row;
+      const int c = p >> 3, piece = p & 7, k = p * 4;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (k < A.d && (n < A.n0 || A.w1 != nullptr))
+        v = ldg4((n < A.n0 ? A.w0 + (size_t)n * A.d : A.w1 + (size_t)(n - A.n0) * A.d) + k);
+      float4 hi, lo;
+      tc_split4(v, hi, lo);
+      const size_t off = (size_t)c * w_chunk_bytes + (size_t)n * 128 + (size_t)((piece ^ (n & 7)) * 16);
+      *reinterpret_cast<float4*>(w_hi + off) = hi;
+      *reinterpret_cast<float4*>(w_lo + off) = lo;
+    }
+  }
+  tc_fence_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  const int first_tile = blockIdx.x, tile_step = gridDim.x;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int tile = first_tile; tile < A.n_tiles; tile += tile_step) {
+        for (int c = 0; c < A.nkc; ++c) {
+          tc_mbar_wait(tc_smem_u32(raw_free + s), ph ^ 1u);
+          tc_mbar_expect_tx(tc_smem_u32(full + s), kTcTileBytes);
+          tc_tma_load_2d(tc_smem_u32(raw0 + (size_t)s * kTcTileBytes), &xmap, c * kTcChunkCols, tile * kTcRows,
+                         tc_smem_u32(full + s));
+          if (++s == P.raw_slots) { s = 0; ph ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer: A from tensor memory, B (split weights) from shared memory =====
+    if (lane == 0) {
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(kTcRows >> 4) << 24);
+      int as = 0;
+      uint32_t aph = 0;
+      int it = 0;
+      for (int tile = first_tile; tile < A.n_tiles; tile += tile_step, ++it) {
+        const int b = it & 1;
+        const uint32_t use = (uint32_t)(it >> 1) & 1u;
+        tc_mbar_wait(tc_smem_u32(acc_empty + b), use ^ 1u);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(b * A.acc_stride);
+        for (int c = 0; c < A.nkc; ++c) {
+          tc_mbar_wait(tc_smem_u32(a_ready + as), aph);
+          tc_fence_after();
+          const uint32_t a_hi = tmem_base + (uint32_t)(P.a_col0 + as * 64);
+          const uint32_t a_lo = a_hi + 32u;
+          const uint32_t b_hi = tc_smem_u32(w_hi + (size_t)c * w_chunk_bytes);
+          const uint32_t b_lo = tc_smem_u32(w_lo + (size_t)c * w_chunk_bytes);
+#pragma unroll
+          for (int k4 = 0; k4 < 4; ++k4) {
+            const uint32_t ko = (uint32_t)k4 * 32u, kc = (uint32_t)k4 * 8u;
+            tc_mma_tf32_ts(tmem_d, a_lo + kc, tc_smem_desc(b_hi + ko), idesc, (c | k4) != 0);   // small terms first
+            tc_mma_tf32_ts(tmem_d, a_hi + kc, tc_smem_desc(b_lo + ko), idesc, 1u);
+            tc_mma_tf32_ts(tmem_d, a_hi + kc, tc_smem_desc(b_hi + ko), idesc, 1u);
+          }
+          tc_commit(tc_smem_u32(a_free + as));
+          if (c == A.nkc - 1) tc_commit(tc_smem_u32(acc_full + b));
+          if (++as == P.a_stages) { as = 0; aph ^= 1u; }
+        }
+      }
+    }
+  } else {
+    // ===== converters (one row = one TMEM lane per thread) + epilogue =====
+    const int quad = warp & 3;
+    const int m = quad * 32 + lane;                              // row of the tile == TMEM lane
+    const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
+    int s = 0, as = 0;
+    uint32_t ph = 0, aph = 0;
+    int it = 0;
+    auto epilogue = [&](int tile, int eit) {
+      const int b = eit & 1;
+      const uint32_t use = (uint32_t)(eit >> 1) & 1u;
+      tc_mbar_wait(tc_smem_u32(acc_full + b), use);
+      tc_fence_after();
+      const int row = tile * kTcRows + m;
+      const uint32_t taddr = tmem_base + lane_base + (uint32_t)(b * A.acc_stride);
+      for (int g = 0; g < N; g += 16) {
+        uint32_t v[16];
+        tc_tmem_ld16(taddr + (uint32_t)g, v);
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4) {
+          const int col = g + 4 * q4;
+          float4 o;
+          o.x = __uint_as_float(v[4 * q4 + 0]) + bias[col + 0];
+          o.y = __uint_as_float(v[4 * q4 + 1]) + bias[col + 1];
+          o.z = __uint_as_float(v[4 * q4 + 2]) + bias[col + 2];
+          o.w = __uint_as_float(v[4 * q4 + 3]) + bias[col + 3];
+          if (col < A.n0) {
+            if (row < A.rows0) *reinterpret_cast<float4*>(A.y0 + (size_t)row * A.ld0 + col) = o;
+          } else {
+            if (row < A.rows1) *reinterpret_cast<float4*>(A.y1 + (size_t)row * A.ld1 + (col - A.n0)) = o;
+          }
+        }
+      }
+      tc_fence_before();
+      tc_mbar_arrive(tc_smem_u32(acc_empty + b));
+    };
+    int prev_tile = -1;
+    for (int tile = first_tile; tile < A.n_tiles; tile += tile_step, ++it) {
+      for (int c = 0; c < A.nkc; ++c) {
+        tc_mbar_wait(tc_smem_u32(full + s), ph);
+        const unsigned char* rowp = raw0 + (size_t)s * kTcTileBytes + (size_t)m * 128;
+        uint32_t hi[32], lo[32];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {                            // logical 16-byte piece j sits at physical piece j ^ (m & 7)
+          const float4 v = *reinterpret_cast<const float4*>(rowp + ((j ^ (m & 7)) * 16));
+          float4 h, l;
+          tc_split4(v, h, l);
+          hi[4 * j + 0] = __float_as_uint(h.x); hi[4 * j + 1] = __float_as_uint(h.y);
+          hi[4 * j + 2] = __float_as_uint(h.z); hi[4 * j + 3] = __float_as_uint(h.w);
+          lo[4 * j + 0] = __float_as_uint(l.x); lo[4 * j + 1] = __float_as_uint(l.y);
+          lo[4 * j + 2] = __float_as_uint(l.z); lo[4 * j + 3] = __float_as_uint(l.w);
+        }
+        tc_mbar_arrive(tc_smem_u32(raw_free + s));               // the slot's bytes are in registers: TMA may refill it
+        tc_mbar_wait(tc_smem_u32(a_free + as), aph ^ 1u);        // the MMAs that read this A stage last time have retired
+        tc_fence_after();
+        const uint32_t acol = tmem_base + lane_base + (uint32_t)(P.a_col0 + as * 64);
+        tc_tmem_st32(acol, hi);
+        tc_tmem_st32(acol + 32u, lo);
+        tc_tmem_wait_st();
+        tc_fence_before();
+        tc_mbar_arrive(tc_smem_u32(a_ready + as));
+        if (++s == P.raw_slots) { s = 0; ph ^= 1u; }
+        if (++as == P.a_stages) { as = 0; aph ^= 1u; }
+      }
+      if (prev_tile >= 0) epilogue(prev_tile, it - 1);
+      prev_tile = tile;
+    }
+    if (prev_tile >= 0) epilogue(prev_tile, it - 1);
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)A.tmem_cols) : "memory");
+  }
+}
+
 // ---- host side --------------------------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -343,7 +574,7 @@ static EncodeTiledFn encode_tiled_fn() {
 // the mma.sync kernel.
 int launch_linear_tc(const float* x, int n_x_rows, int d, const float* w0, const float* b0, int n0, float* y0, int rows0,
                      int ld0, const float* w1, const float* b1, int n1, float* y1, int rows1, int ld1,
-                     cudaStream_t stream) {
+                     cudaStream_t stream, int variant) {
   const int N = n0 + n1;
   if (n_x_rows <= 0) return GRAND_OK;
   if ((d & 3) != 0 || d <= 0 || d > kTcMaxChunks * kTcChunkCols) return GRAND_EUNSUPPORTED;
@@ -377,8 +608,8 @@ int launch_linear_tc(const float* x, int n_x_rows, int d, const float* w0, const
     static int pf = -1;                  // GRAND_TC_PREFETCH=<tiles>: measurement switch, read once
     if (pf < 0) {
       const char* e = getenv("GRAND_TC_PREFETCH");
-      pf = e != nullptr ? atoi(e) : 2;
-      if (pf < 0 || pf > 8) pf = 2;
+      pf = e != nullptr ? atoi(e) : 0;   // measured on B200 (profiles/r02v_*): 0 -> 45.4 us, 2 -> 49.1, 4 -> 50.0: off
+      if (pf < 0 || pf > 8) pf = 0;
     }
     A.prefetch_tiles = pf;
   }
@@ -394,10 +625,33 @@ int launch_linear_tc(const float* x, int n_x_rows, int d, const float* w0, const
                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   GRAND_REQUIRE(cr == CUDA_SUCCESS, GRAND_ECUDA, "linear_tc: cuTensorMapEncodeTiled failed (%d) for [%d, %d]", (int)cr,
                 n_x_rows, d);
-  // per device and cheap: set on every launch (no process-wide "already done" flag)
-  GRAND_CUDA_OK(cudaFuncSetAttribute(linear_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int grid = num_sms();
   if (grid > A.n_tiles) grid = A.n_tiles;
+  // variant 3: split chunks in tensor memory (needs 2 accumulators + >= 2 A stages in the 512 columns)
+  const int acc_stride_tm = (N + 31) & ~31;
+  if (variant >= 3 && 2 * acc_stride_tm + 2 * 64 <= 512) {
+    TmArgs P;
+    P.t = A;
+    P.t.tmem_cols = 512;
+    P.t.acc_stride = acc_stride_tm;
+    P.a_col0 = 2 * acc_stride_tm;
+    P.a_stages = (512 - P.a_col0) / 64;
+    if (P.a_stages > kTmMaxA) P.a_stages = kTmMaxA;
+    const size_t tail_tm = 1024 + (2 * kTmMaxRaw + 2 * kTmMaxA + 4) * 8 + 16 + (size_t)N * 4;
+    int raw = (int)((budget - w_bytes - tail_tm) / kTcTileBytes);
+    if (raw > kTmMaxRaw) raw = kTmMaxRaw;
+    if (raw >= 2) {
+      P.raw_slots = raw;
+      const size_t smem_tm = w_bytes + (size_t)raw * kTcTileBytes + tail_tm;
+      GRAND_CUDA_OK(cudaFuncSetAttribute(linear_tm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tm));
+      linear_tm_kernel<<<grid, kTcThreads, smem_tm, stream>>>(xmap, P);
+      GRAND_CUDA_OK(cudaGetLastError());
+      count_launch();
+      return GRAND_OK;
+    }
+  }
+  // per device and cheap: set on every launch (no process-wide "already done" flag)
+  GRAND_CUDA_OK(cudaFuncSetAttribute(linear_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   linear_tc_kernel<<<grid, kTcThreads, smem, stream>>>(xmap, A);
   GRAND_CUDA_OK(cudaGetLastError());
   count_launch();

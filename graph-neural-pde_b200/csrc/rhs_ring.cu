@@ -338,6 +338,9 @@ bool ring_kernel_ok(int mode, const RhsArgs& A) {
   // fixed weights (GRAND-l) have no scoring phase for the copies to overlap with: the register gathers are faster there
   // (ogbn-arxiv shape: 134 vs 144 us), the attention modes are faster on the ring (265 vs 288)
   if (sel == 0 && mode == MODE_WEIGHT) return false;
+  // small graphs (everything L2-resident, a launch lasts as long as its longest unit): 2 x 10 register-gather warps per SM
+  // finish sooner than 14 ring warps -- Photo 111 vs 139 us per evaluation, Cora 44.4 vs 45.5 (profiles/r02v_small.txt)
+  if (sel == 0 && A.g.n_edges < (1 << 20)) return false;
   if (A.d > kWarp * 4 || (A.d & 3) != 0) return false;
   if ((reinterpret_cast<uintptr_t>(A.x) & 15) != 0) return false;
   return true;

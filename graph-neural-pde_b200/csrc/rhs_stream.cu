@@ -29,7 +29,7 @@
 namespace grand {
 
 #ifndef GRAND_EPI_COEF_ONCE
-#define GRAND_EPI_COEF_ONCE 0   // measurement switch (tools/build_variants.sh)
+#define GRAND_EPI_COEF_ONCE 1   // 0: one test per coefficient (measured 2-4 us slower per launch, profiles/r02v_ab.txt)
 #endif
 #ifndef GRAND_STREAM_THREADS
 #define GRAND_STREAM_THREADS 320

@@ -203,7 +203,8 @@ int grand_project_qk(const float* x, int32_t n_rows, int32_t n_cols, const grand
 int grand_linear(const float* x, int32_t n_rows, int32_t d_in, const float* w, const float* b, int32_t d_out, float* y,
                  int32_t ldy, void* stream);
 
-/* Measurement switch (process-wide): which kernel computes the projections -- 2 tcgen05 (csrc/project_tc.cu), 1 mma.sync
+/* Measurement switch (process-wide): which kernel computes the projections -- 3 tcgen05 with the split X chunks in tensor
+ * memory, 2 tcgen05 with all operands in shared memory (both csrc/project_tc.cu), 1 mma.sync
  * (csrc/project_mma.cu), 0 fp32 FFMA (csrc/project.cu), -1 back to the default (or the GRAND_PROJ environment variable).
  * A kernel that does not cover a shape hands over to the next. */
 int grand_set_projection_impl(int32_t impl);

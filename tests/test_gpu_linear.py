@@ -27,7 +27,7 @@ def _rel(got, want):
   return float((got.double() - want).abs().max() / want.abs().max())
 
 
-@pytest.mark.parametrize('impl', [0, 1, 2])
+@pytest.mark.parametrize('impl', [0, 1, 2, 3])
 @pytest.mark.parametrize('n_rows,n_cols,d,ad', [
   (1000, 1000, 128, 32),      # ogbn-arxiv layout (4 heads x 8)
   (300, 517, 80, 16),         # fewer query rows than key rows (a shard: own rows | halo), d not a multiple of 32
@@ -57,7 +57,7 @@ def test_projection_kernels_vs_fp64(impl, n_rows, n_cols, d, ad):
   assert torch.isnan(q[n_rows:]).all() and torch.isnan(k[n_cols:]).all()      # nothing stored past the row counts
 
 
-@pytest.mark.parametrize('impl', [1, 2])
+@pytest.mark.parametrize('impl', [1, 2, 3])
 @pytest.mark.parametrize('rows,d_in,d_out,bias', [
   (1000, 128, 128, True), (1000, 128, 40, True), (777, 40, 128, False), (257, 1433, 80, True), (100, 80, 7, True),
   (130, 64, 64, True), (5, 8, 16, True),

@@ -46,7 +46,7 @@ def project(n_rows, n_cols, d, ad, seed=0):
   want_k = (x.double() @ wk.double().t() + bk.double())
   st = N.current_stream(DEV)
   line = 'project n_rows %7d n_cols %7d d %4d ad %3d:' % (n_rows, n_cols, d, ad)
-  for impl, name in ((1, 'mma'), (2, 'tc')):
+  for impl, name in ((1, 'mma'), (2, 'tc'), (3, 'tm')):
     N.check(N.lib().grand_set_projection_impl(impl))
     q = torch.full((n_rows, ad), float('nan'), device=DEV)
     k = torch.full((n_cols, ad), float('nan'), device=DEV)
@@ -70,7 +70,7 @@ def linear(rows, d_in, d_out, seed=0, bias=True):
   want = x.double() @ w.double().t() + (b.double() if bias else 0)
   st = N.current_stream(DEV)
   line = 'linear  rows %7d d_in %5d d_out %4d:' % (rows, d_in, d_out)
-  for impl, name in ((1, 'fp32'), (2, 'tc')):
+  for impl, name in ((1, 'fp32'), (2, 'tc'), (3, 'tm')):
     N.check(N.lib().grand_set_projection_impl(impl))
     y = torch.full((rows, d_out), float('nan'), device=DEV)
 
