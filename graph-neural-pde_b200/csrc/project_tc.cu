@@ -77,11 +77,6 @@ __device__ __forceinline__ void tc_fence_async_smem() { asm volatile("fence.prox
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
-__device__ __forceinline__ void tc_bulk_copy_row(uint32_t dst, const float* src, uint32_t bytes, uint32_t bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
-               "r"(bytes), "r"(bar)
-               : "memory");
-}
 __device__ __forceinline__ void tc_tma_prefetch_2d(const CUtensorMap* map, int c0, int c1) {
   asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];" ::"l"(reinterpret_cast<uint64_t>(map)), "r"(c0),
                "r"(c1)
@@ -348,28 +343,23 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
 
 // ---- variant 2: the split X chunks live in TENSOR MEMORY, shared memory only holds what TMA lands ---------------------------
 // The shared-memory version above moves every X byte through shared memory five times (TMA write, converter read, two
-// converter writes, ~three tensor-core reads: ~0.5 MB per 128-row tile) and asks the copy engine for 512 requests of 128
-// bytes per tile; the ncu capture (profiles/r02x_*) shows it waiting on its barriers at 2.3 TB/s, the same time as
-// mma.sync.  Two changes: (1) a converter thread owns ONE row of the tile (= one TMEM lane): it reads its row from
-// the landing buffer, splits it and stores hi / lo straight into TENSOR MEMORY (tcgen05.st 32x32b.x32), from where
-// tcgen05.mma takes its A operand -- the tensor cores read only W from shared memory; (2) X arrives as ONE bulk copy per
-// row (cp.async.bulk, 512 bytes at d = 128: the copy engine's cost is per request, measured ~10-16 cycles each whatever
-// the size), into rows skewed by 16 bytes so that the row-per-thread reads are bank-conflict free.  Whole tiles are
-// double buffered.
+// converter writes, ~three tensor-core reads): ~0.5 MB per 128-row tile, which is what bounds it (36 us on ogbn-arxiv,
+// no faster than mma.sync).  Here a converter thread owns ONE row of the tile (= one TMEM lane): it reads its 128 bytes
+// of the landed chunk (8 LDS.128, conflict-free under the 128-byte swizzle), splits them and stores hi / lo straight
+// into tensor memory (tcgen05.st 32x32b.x32), from where tcgen05.mma takes its A operand.  The landing buffer is free
+// as soon as it has been read, so shared memory holds 10 x 16 KB of loads in flight instead of 5 stages; the tensor
+// cores read only W from shared memory.
 //   TMEM columns: [0, 2 acc_stride) two accumulators, then a_stages x (32 hi | 32 lo).
-constexpr int kTmMaxRaw = 4;
-constexpr int kTmRowStride = 512 + 16;             // landing rows are skewed by 16 bytes: conflict-free row-per-thread reads
-constexpr int kTmTileBytes = kTcRows * kTmRowStride;
+constexpr int kTmMaxRaw = 12;
 constexpr int kTmMaxA = 6;
 
 struct TmArgs {
   TcArgs t;
-  const float* x;
   int raw_slots, a_stages, a_col0;
 };
 
 __global__ void __launch_bounds__(kTcThreads, 1)
-linear_tm_kernel(const __grid_constant__ TmArgs P) {
+linear_tm_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ TmArgs P) {
   extern __shared__ __align__(1024) unsigned char tc_smem[];
   const TcArgs& A = P.t;
   unsigned char* base = tc_smem + ((1024u - (tc_smem_u32(tc_smem) & 1023u)) & 1023u);
@@ -378,9 +368,9 @@ linear_tm_kernel(const __grid_constant__ TmArgs P) {
   unsigned char* w_hi = base;
   unsigned char* w_lo = w_hi + (size_t)A.nkc * w_chunk_bytes;
   unsigned char* raw0 = w_lo + (size_t)A.nkc * w_chunk_bytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(raw0 + (size_t)P.raw_slots * kTmTileBytes);
-  uint64_t* full = bars;                          // [raw_slots] the tile's rows have landed
-  uint64_t* raw_free = full + kTmMaxRaw;          // [raw_slots] the 128 converter threads have read the whole tile
+  uint64_t* bars = reinterpret_cast<uint64_t*>(raw0 + (size_t)P.raw_slots * kTcTileBytes);
+  uint64_t* full = bars;                          // [raw_slots] TMA landed
+  uint64_t* raw_free = full + kTmMaxRaw;          // [raw_slots] the 128 converter threads have read the slot
   uint64_t* a_ready = raw_free + kTmMaxRaw;       // [a_stages]  hi / lo of a chunk are in tensor memory (128 arrivals)
   uint64_t* a_free = a_ready + kTmMaxA;           // [a_stages]  the MMAs reading the stage retired (tcgen05.commit)
   uint64_t* acc_full = a_free + kTmMaxA;          // [2]
@@ -437,25 +427,18 @@ linear_tm_kernel(const __grid_constant__ TmArgs P) {
   const int first_tile = blockIdx.x, tile_step = gridDim.x;
 
   if (warp == 0) {
-    // ===== producer: one bulk copy per ROW (the copy engine's cost is per request, not per byte: 512-byte requests) =====
-    {
+    // ===== TMA producer =====
+    if (lane == 0) {
       int s = 0;
       uint32_t ph = 0;
-      const uint32_t row_bytes = (uint32_t)A.d * 4u;
       for (int tile = first_tile; tile < A.n_tiles; tile += tile_step) {
-        tc_mbar_wait(tc_smem_u32(raw_free + s), ph ^ 1u);
-        const int rows_here = min(kTcRows, A.n_x_rows - tile * kTcRows);
-        if (lane == 0) tc_mbar_expect_tx(tc_smem_u32(full + s), (uint32_t)rows_here * row_bytes);
-        __syncwarp();
-        unsigned char* buf = raw0 + (size_t)s * kTmTileBytes;
-#pragma unroll
-        for (int i = 0; i < kTcRows / kWarp; ++i) {
-          const int r = lane + i * kWarp;
-          if (r < rows_here)
-            tc_bulk_copy_row(tc_smem_u32(buf + (size_t)r * kTmRowStride), P.x + (size_t)(tile * kTcRows + r) * A.d, row_bytes,
-                             tc_smem_u32(full + s));
+        for (int c = 0; c < A.nkc; ++c) {
+          tc_mbar_wait(tc_smem_u32(raw_free + s), ph ^ 1u);
+          tc_mbar_expect_tx(tc_smem_u32(full + s), kTcTileBytes);
+          tc_tma_load_2d(tc_smem_u32(raw0 + (size_t)s * kTcTileBytes), &xmap, c * kTcChunkCols, tile * kTcRows,
+                         tc_smem_u32(full + s));
+          if (++s == P.raw_slots) { s = 0; ph ^= 1u; }
         }
-        if (++s == P.raw_slots) { s = 0; ph ^= 1u; }
       }
     }
   } else if (warp == 1) {
@@ -530,15 +513,12 @@ linear_tm_kernel(const __grid_constant__ TmArgs P) {
     int prev_tile = -1;
     for (int tile = first_tile; tile < A.n_tiles; tile += tile_step, ++it) {
       for (int c = 0; c < A.nkc; ++c) {
-        if (c == 0) tc_mbar_wait(tc_smem_u32(full + s), ph);
-        // this thread's row of the tile; rows are 528 bytes apart, so the 8 threads of an LDS.128 phase hit 8 different
-        // bank groups
-        const unsigned char* rowp = raw0 + (size_t)s * kTmTileBytes + (size_t)m * kTmRowStride + (size_t)c * 128;
+        tc_mbar_wait(tc_smem_u32(full + s), ph);
+        const unsigned char* rowp = raw0 + (size_t)s * kTcTileBytes + (size_t)m * 128;
         uint32_t hi[32], lo[32];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (c * kTcChunkCols + 4 * j < A.d) v = *reinterpret_cast<const float4*>(rowp + j * 16);
+        for (int j = 0; j < 8; ++j) {                            // logical 16-byte piece j sits at physical piece j ^ (m & 7)
+          const float4 v = *reinterpret_cast<const float4*>(rowp + ((j ^ (m & 7)) * 16));
           float4 h, l;
           tc_split4(v, h, l);
           hi[4 * j + 0] = __float_as_uint(h.x); hi[4 * j + 1] = __float_as_uint(h.y);
@@ -546,7 +526,7 @@ linear_tm_kernel(const __grid_constant__ TmArgs P) {
           lo[4 * j + 0] = __float_as_uint(l.x); lo[4 * j + 1] = __float_as_uint(l.y);
           lo[4 * j + 2] = __float_as_uint(l.z); lo[4 * j + 3] = __float_as_uint(l.w);
         }
-        if (c == A.nkc - 1) tc_mbar_arrive(tc_smem_u32(raw_free + s));   // the tile is in registers / TMEM: refill the buffer
+        tc_mbar_arrive(tc_smem_u32(raw_free + s));               // the slot's bytes are in registers: TMA may refill it
         tc_mbar_wait(tc_smem_u32(a_free + as), aph ^ 1u);        // the MMAs that read this A stage last time have retired
         tc_fence_after();
         const uint32_t acol = tmem_base + lane_base + (uint32_t)(P.a_col0 + as * 64);
@@ -555,9 +535,9 @@ linear_tm_kernel(const __grid_constant__ TmArgs P) {
         tc_tmem_wait_st();
         tc_fence_before();
         tc_mbar_arrive(tc_smem_u32(a_ready + as));
+        if (++s == P.raw_slots) { s = 0; ph ^= 1u; }
         if (++as == P.a_stages) { as = 0; aph ^= 1u; }
       }
-      if (++s == P.raw_slots) { s = 0; ph ^= 1u; }
       if (prev_tile >= 0) epilogue(prev_tile, it - 1);
       prev_tile = tile;
     }
@@ -658,14 +638,13 @@ int launch_linear_tc(const float* x, int n_x_rows, int d, const float* w0, const
     P.a_stages = (512 - P.a_col0) / 64;
     if (P.a_stages > kTmMaxA) P.a_stages = kTmMaxA;
     const size_t tail_tm = 1024 + (2 * kTmMaxRaw + 2 * kTmMaxA + 4) * 8 + 16 + (size_t)N * 4;
-    int raw = (int)((budget - w_bytes - tail_tm) / kTmTileBytes);
+    int raw = (int)((budget - w_bytes - tail_tm) / kTcTileBytes);
     if (raw > kTmMaxRaw) raw = kTmMaxRaw;
-    if (raw >= 1) {
+    if (raw >= 2) {
       P.raw_slots = raw;
-      P.x = x;
-      const size_t smem_tm = w_bytes + (size_t)raw * kTmTileBytes + tail_tm;
+      const size_t smem_tm = w_bytes + (size_t)raw * kTcTileBytes + tail_tm;
       GRAND_CUDA_OK(cudaFuncSetAttribute(linear_tm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tm));
-      linear_tm_kernel<<<grid, kTcThreads, smem_tm, stream>>>(P);
+      linear_tm_kernel<<<grid, kTcThreads, smem_tm, stream>>>(xmap, P);
       GRAND_CUDA_OK(cudaGetLastError());
       count_launch();
       return GRAND_OK;
