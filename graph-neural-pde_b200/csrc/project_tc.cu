@@ -118,6 +118,13 @@ __device__ __forceinline__ void tc_tmem_st32(uint32_t taddr, const uint32_t (&v)
       "r"(v[31])
       : "memory");
 }
+__device__ __forceinline__ void tc_tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
+      "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]),
+      "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+      : "memory");
+}
 __device__ __forceinline__ void tc_tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
@@ -351,6 +358,8 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
 // cores read only W from shared memory.
 //   TMEM columns: [0, 2 acc_stride) two accumulators, then a_stages x (32 hi | 32 lo).
 constexpr int kTmMaxRaw = 12;
+constexpr int kTmConvThreads = 256;                 // 8 converter / epilogue warps
+constexpr int kTmThreads = 64 + kTmConvThreads;
 constexpr int kTmMaxA = 6;
 
 struct TmArgs {
@@ -358,7 +367,7 @@ struct TmArgs {
   int raw_slots, a_stages, a_col0;
 };
 
-__global__ void __launch_bounds__(kTcThreads, 1)
+__global__ void __launch_bounds__(kTmThreads, 1)
 linear_tm_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ TmArgs P) {
   extern __shared__ __align__(1024) unsigned char tc_smem[];
   const TcArgs& A = P.t;
@@ -382,15 +391,15 @@ linear_tm_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
   if (tid == 0) {
     for (int s = 0; s < P.raw_slots; ++s) {
       tc_mbar_init(tc_smem_u32(full + s), 1);
-      tc_mbar_init(tc_smem_u32(raw_free + s), kTcConvThreads);
+      tc_mbar_init(tc_smem_u32(raw_free + s), kTmConvThreads);
     }
     for (int s = 0; s < P.a_stages; ++s) {
-      tc_mbar_init(tc_smem_u32(a_ready + s), kTcConvThreads);
+      tc_mbar_init(tc_smem_u32(a_ready + s), kTmConvThreads);
       tc_mbar_init(tc_smem_u32(a_free + s), 1);
     }
     for (int b = 0; b < 2; ++b) {
       tc_mbar_init(tc_smem_u32(acc_full + b), 1);
-      tc_mbar_init(tc_smem_u32(acc_empty + b), kTcConvThreads);
+      tc_mbar_init(tc_smem_u32(acc_empty + b), kTmConvThreads);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -400,13 +409,13 @@ linear_tm_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  for (int o = tid; o < N; o += kTcThreads) {
+  for (int o = tid; o < N; o += kTmThreads) {
     const float* b = o < A.n0 ? A.b0 : A.b1;
     bias[o] = b != nullptr ? __ldg(b + (o < A.n0 ? o : o - A.n0)) : 0.f;
   }
   {
     const int c4_per_row = A.nkc * 8;
-    for (int idx = tid; idx < N * c4_per_row; idx += kTcThreads) {
+    for (int idx = tid; idx < N * c4_per_row; idx += kTmThreads) {
       const int n = idx / c4_per_row, p = idx - n * c4_per_row;
       const int c = p >> 3, piece = p & 7, k = p * 4;
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -475,8 +484,9 @@ linear_tm_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
       }
     }
   } else {
-    // ===== converters (one row = one TMEM lane per thread) + epilogue =====
+    // ===== converters + epilogue: 8 warps, two per TMEM lane quadrant; a thread owns HALF of a row's chunk (16 columns) =====
     const int quad = warp & 3;
+    const int half = (warp - 2) >> 2;                            // warps 2-5: columns [0, 16) of a chunk, warps 6-9: [16, 32)
     const int m = quad * 32 + lane;                              // row of the tile == TMEM lane
     const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
     int s = 0, as = 0;
@@ -489,7 +499,7 @@ linear_tm_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
       tc_fence_after();
       const int row = tile * kTcRows + m;
       const uint32_t taddr = tmem_base + lane_base + (uint32_t)(b * A.acc_stride);
-      for (int g = 0; g < N; g += 16) {
+      for (int g = 16 * half; g < N; g += 32) {                   // the two warps of a quadrant alternate 16-column groups
         uint32_t v[16];
         tc_tmem_ld16(taddr + (uint32_t)g, v);
 #pragma unroll
@@ -515,23 +525,24 @@ linear_tm_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
       for (int c = 0; c < A.nkc; ++c) {
         tc_mbar_wait(tc_smem_u32(full + s), ph);
         const unsigned char* rowp = raw0 + (size_t)s * kTcTileBytes + (size_t)m * 128;
-        uint32_t hi[32], lo[32];
+        uint32_t hi[16], lo[16];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {                            // logical 16-byte piece j sits at physical piece j ^ (m & 7)
+        for (int jj = 0; jj < 4; ++jj) {                         // logical 16-byte piece j sits at physical piece j ^ (m & 7)
+          const int j = 4 * half + jj;
           const float4 v = *reinterpret_cast<const float4*>(rowp + ((j ^ (m & 7)) * 16));
           float4 h, l;
           tc_split4(v, h, l);
-          hi[4 * j + 0] = __float_as_uint(h.x); hi[4 * j + 1] = __float_as_uint(h.y);
-          hi[4 * j + 2] = __float_as_uint(h.z); hi[4 * j + 3] = __float_as_uint(h.w);
-          lo[4 * j + 0] = __float_as_uint(l.x); lo[4 * j + 1] = __float_as_uint(l.y);
-          lo[4 * j + 2] = __float_as_uint(l.z); lo[4 * j + 3] = __float_as_uint(l.w);
+          hi[4 * jj + 0] = __float_as_uint(h.x); hi[4 * jj + 1] = __float_as_uint(h.y);
+          hi[4 * jj + 2] = __float_as_uint(h.z); hi[4 * jj + 3] = __float_as_uint(h.w);
+          lo[4 * jj + 0] = __float_as_uint(l.x); lo[4 * jj + 1] = __float_as_uint(l.y);
+          lo[4 * jj + 2] = __float_as_uint(l.z); lo[4 * jj + 3] = __float_as_uint(l.w);
         }
         tc_mbar_arrive(tc_smem_u32(raw_free + s));               // the slot's bytes are in registers: TMA may refill it
         tc_mbar_wait(tc_smem_u32(a_free + as), aph ^ 1u);        // the MMAs that read this A stage last time have retired
         tc_fence_after();
         const uint32_t acol = tmem_base + lane_base + (uint32_t)(P.a_col0 + as * 64);
-        tc_tmem_st32(acol, hi);
-        tc_tmem_st32(acol + 32u, lo);
+        tc_tmem_st16(acol + (uint32_t)(16 * half), hi);
+        tc_tmem_st16(acol + 32u + (uint32_t)(16 * half), lo);
         tc_tmem_wait_st();
         tc_fence_before();
         tc_mbar_arrive(tc_smem_u32(a_ready + as));
@@ -644,7 +655,7 @@ int launch_linear_tc(const float* x, int n_x_rows, int d, const float* w0, const
       P.raw_slots = raw;
       const size_t smem_tm = w_bytes + (size_t)raw * kTcTileBytes + tail_tm;
       GRAND_CUDA_OK(cudaFuncSetAttribute(linear_tm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tm));
-      linear_tm_kernel<<<grid, kTcThreads, smem_tm, stream>>>(xmap, P);
+      linear_tm_kernel<<<grid, kTmThreads, smem_tm, stream>>>(xmap, P);
       GRAND_CUDA_OK(cudaGetLastError());
       count_launch();
       return GRAND_OK;
