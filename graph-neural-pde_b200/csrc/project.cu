@@ -13,7 +13,8 @@
 namespace grand {
 
 #ifndef GRAND_PROJ_DEFAULT
-#define GRAND_PROJ_DEFAULT 2   // tcgen05 kernel (validated on B200: profiles/r02u_proj_ab.txt); shapes it does not cover fall through
+#define GRAND_PROJ_DEFAULT 3   // tcgen05 with the split X chunks in tensor memory (validated on B200: profiles/r02w-y_*); shapes it
+                               // does not cover fall through to 2 (operands in shared memory), 1 (mma.sync), 0 (FFMA)
 #endif
 
 constexpr int kProjThreads = 256;
@@ -147,8 +148,8 @@ int launch_linear_tc(const float* x, int n_x_rows, int d, const float* w0, const
                      int ld0, const float* w1, const float* b1, int n1, float* y1, int rows1, int ld1,
                      cudaStream_t stream, int variant);
 
-// Which kernel computes the projections: 2 = tcgen05 / TMEM / TMA (project_tc.cu), 1 = mma.sync 3xTF32 (project_mma.cu),
-// 0 = fp32 FFMA.  A kernel that does not cover a shape hands over to the next one.  GRAND_PROJ=tc|mma|ffma is read once;
+// Which kernel computes the projections: 3 / 2 = tcgen05 / TMEM / TMA (project_tc.cu; 3 keeps the split X chunks in
+// tensor memory), 1 = mma.sync 3xTF32 (project_mma.cu), 0 = fp32 FFMA.  A kernel that does not cover a shape hands over to the next one.  GRAND_PROJ=tm|tc|mma|ffma is read once;
 // grand_set_projection_impl overrides it at run time (in-process A/B measurements).
 static int g_proj_impl = -1;
 int projection_impl() {

@@ -1,14 +1,13 @@
-# End-of-round validation on one B200: GPU tests, smoke, the default bench (with CPU baseline and the other BASELINE
-# configurations) and its reference arm, the ncu launch list of a short bench run and one full capture of the edge kernel
-# and of the projection.  Everything lands in gpurun_out/ (scratch); the summaries that matter are copied into profiles/.
+# End-of-round validation on one B200: GPU tests, smoke, the default bench (CPU baseline + other configurations) and its
+# reference arm, the ncu launch list of a short bench run and one full capture of the edge kernel and of the projection.
 set -u
 cd /root/repo
 TAG=${1:-r02z}
-O=gpurun_out
-timeout 600 python -m pytest tests -m gpu -q 2>&1 | tail -2 > $O/${TAG}_pytest.txt; cat $O/${TAG}_pytest.txt
-timeout 120 python -c "import __graft_entry__ as g; g.smoke(); print('SMOKE OK')" 2>&1 | tail -3
-timeout 600 python bench.py > $O/${TAG}_bench_arxiv_n1_full.json 2> $O/${TAG}_bench.err || tail -3 $O/${TAG}_bench.err
-timeout 400 python bench.py --impl reference --steps 5 --warmup 1 > $O/${TAG}_bench_reference.json 2>> $O/${TAG}_bench.err
+O=gpurun_out; mkdir -p $O
+timeout 900 python -m pytest tests -m gpu -q 2>&1 | tail -3 | tee $O/${TAG}_pytest.txt
+timeout 200 python -c "import __graft_entry__ as g; g.smoke(); print('SMOKE OK')" 2>&1 | tail -3
+timeout 700 python bench.py > $O/${TAG}_bench_arxiv_n1_full.json 2> $O/${TAG}_bench.err || tail -3 $O/${TAG}_bench.err
+timeout 400 python bench.py --impl reference --steps 3 --warmup 1 > $O/${TAG}_bench_reference.json 2>> $O/${TAG}_bench.err
 python - "$TAG" <<'PY'
 import json, sys
 tag = sys.argv[1]
@@ -24,11 +23,10 @@ try:
 except Exception as e:
     print('bench summary FAILED', e)
 PY
-timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'grand' -c 120 --csv --log-file $O/${TAG}_launches_arxiv.csv \
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'rhs_|linear_t|project_|lseg_|split_|segment_|edge_' -c 150 --csv --log-file $O/${TAG}_launches_arxiv.csv \
   python bench.py --steps 1 --warmup 1 --skip-cpu --no-others --repeats 1 > /dev/null 2>&1
-timeout 300 ncu --set full --clock-control none --import-source on -k regex:rhs_stream_kernel -s 6 -c 1 -f -o $O/${TAG}_rhs_stream \
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:rhs_ring_kernel -s 6 -c 1 -f -o $O/${TAG}_rhs_ring \
   python bench.py --steps 1 --warmup 1 --skip-cpu --no-others --repeats 1 > /dev/null 2>&1
-timeout 300 ncu --set full --clock-control none --import-source on -k regex:project_qk -s 6 -c 1 -f -o $O/${TAG}_project \
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:linear_tm_kernel -s 6 -c 1 -f -o $O/${TAG}_linear_tm \
   python bench.py --steps 1 --warmup 1 --skip-cpu --no-others --repeats 1 > /dev/null 2>&1
-timeout 60 ./tools/l2_probe > $O/${TAG}_l2_probe.txt 2>&1
 ls -la $O/${TAG}_* | awk '{print $5, $9}'
