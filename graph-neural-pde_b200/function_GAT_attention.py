@@ -4,7 +4,8 @@ SpGraphAttentionLayer :70-119), one of the "next" rows of SURVEY.md 8(f).4.
 The additive scorer  e_ij = LeakyReLU(a_src . h_i + a_dst . h_j),  h = x W split into heads, is score type
 GRAND_SCORE_GAT of the general attention pipeline (csrc/attention.cuh): Q = K = x W, the vector `a` and the slope travel
 as `kernel_scalars`.  With mix_features off the reference averages H separate spmm's (:38-42); by linearity that is the
-spmm of the head-mean attention, i.e. the same aggregation kernel the transformer function uses.
+spmm of the head-mean attention, i.e. the same aggregation kernel the transformer function uses.  With mix_features on
+(:31-37) the same aggregation runs on x W (width attention_dim) between two dense layers (grand_linear).
 """
 import torch
 from torch import nn
@@ -81,10 +82,34 @@ class ODEFuncAtt(ODEFunc):
     self.d_k = self.multihead_att_layer.d_k
     self.in_features, self.out_features = in_features, out_features
 
-  def _check(self):
-    if self.opt['mix_features']:
-      raise NotImplementedError('function=GAT with mix_features=True (aggregate x W, then Wout; reference :32-37) is not '
-                                'built; the default mix_features=False path is')
+  def per_call_only(self):
+    """mix_features (reference :31-37) is three launches around two dense layers per evaluation -- attention weights,
+    aggregation of x W, product with Wout -- not the single fused RHS launch: the solvers then drive `forward` stage by
+    stage (odeint.odeint) instead of the fused integration."""
+    return bool(self.opt['mix_features'])
+
+  def _mix_features_rhs(self, x):
+    """f = alpha (mean_h(A_h (x W)) Wout - x) + beta x0.  By linearity the mean over the heads' spmm's is ONE aggregation
+    with the head-mean attention (the weights the Laplacian kernel takes), run at width attention_dim."""
+    from .linear import linear_forward
+    layer = self.multihead_att_layer
+    engine = self.engine(x)
+    _, _, mean_csr = engine.attention_weights(layer.spec(engine), x, want_attention=False, want_prods=False,
+                                              want_mean_csr=True)
+    wx = linear_forward(x, layer.W.detach().t().contiguous(), None)                      # [N, ad]   (:106)
+    cached = getattr(self, '_engine_ad', None)
+    if cached is None or cached[0] is not engine:
+      cached = (engine, RhsEngine(engine.plan, layer.attention_dim))
+      self._engine_ad = cached
+    one = torch.ones((), dtype=torch.float32, device=x.device)
+    r = torch.empty_like(wx)
+    cached[1].rhs_laplacian(mean_csr, wx, RhsEngine.epilogue(one, None, None, True, f_out=r))   # r = A wx - wx
+    ax = linear_forward(r + wx, layer.Wout.detach().t().contiguous(), None)              # [N, d]    (:36)
+    alpha = self.alpha_train.detach() if self.opt['no_alpha_sigmoid'] else torch.sigmoid(self.alpha_train.detach())
+    f = alpha * (ax - x)
+    if self.opt['add_source']:
+      f = f + self.beta_train.detach() * self.x0
+    return f
 
   def residual_epilogue(self, engine, x0_buffer, **outputs):
     x0 = x0_buffer if self.opt['add_source'] else None
@@ -92,7 +117,7 @@ class ODEFuncAtt(ODEFunc):
                               **outputs)
 
   def native_description(self, engine):
-    self._check()
+    assert not self.opt['mix_features'], 'mix_features runs stage by stage (per_call_only)'
     return self.multihead_att_layer.spec(engine), None
 
   def stage_x0(self, engine):
@@ -103,12 +128,13 @@ class ODEFuncAtt(ODEFunc):
     return buf
 
   def forward(self, t, x):  # t is needed when called by the integrator
-    self._check()
     self._bump_nfe()
     N.require_cuda(x, 'x')
     if needs_grad(self, x):
       raise NotImplementedError('grand_b200 backward is built for the transformer (scaled_dot) and Laplacian functions')
     x = x.contiguous()
+    if self.opt['mix_features']:
+      return self._mix_features_rhs(x)
     engine = self.engine(x)
     f = torch.empty_like(x)
     engine.rhs_attention(self.multihead_att_layer.spec(engine), x,

@@ -341,7 +341,10 @@ def odeint(func, y0, t, *, rtol=1e-7, atol=1e-9, method=None, options=None, even
   (training with adjoint=False): the same solvers with every RHS evaluation as one autograd node."""
   method, options = _check_call(y0, method, options, event_fn)
   _require_native(func)
-  if AG.needs_grad(func, y0):
+  per_call = getattr(func, 'per_call_only', None)
+  if AG.needs_grad(func, y0) or (per_call is not None and per_call()):
+    # every RHS evaluation is one call of func.forward (an autograd node when gradients are required; several launches
+    # for the functions that have no single fused RHS launch, e.g. GAT with mix_features)
     if method in FIXED_METHODS:
       _, grid = fixed_grid_dts(float(t[0]), float(t[-1]), options['step_size'])
       return AG.odeint_fixed_autograd(func, y0, t, method, grid)

@@ -26,7 +26,7 @@ def pytest_collection_modifyitems(config, items):
 @pytest.fixture(scope='session')
 def golden():
   cases = {}
-  for name in ('golden_v1.pt', 'golden_v2.pt', 'golden_v3.pt'):   # v2: GAT + hard attention, v3: model shell
+  for name in ('golden_v1.pt', 'golden_v2.pt', 'golden_v3.pt', 'golden_v4.pt'):   # v2: GAT + hard attention, v3: model shell, v4: GAT mix_features
     part = torch.load(os.path.join(ROOT, 'tests', 'golden', name), map_location='cpu', weights_only=False)
     assert not set(part) & set(cases)
     cases.update(part)
