@@ -159,30 +159,47 @@ class LaplacianRhsFn(torch.autograd.Function):
 
 class FrozenAttentionFn(torch.autograd.Function):
   """AttODEblock.get_attention_weights as a differentiable node (reference src/block_transformer_attention.py:28-39):
-  (x0, Wq, bq, Wk, bk) -> (attention[E, H] in caller order, not differentiable; mean_h attention[E] in CSR order,
+  (x0, layer parameters...) -> (attention[E, H] in caller order, not differentiable; mean_h attention[E] in CSR order,
   differentiable).  The Laplacian function integrates with the second output (FrozenLaplacianRhsFn); its gradient sums
-  over the RHS evaluations and comes back here once: softmax backward at x0, then the dense tails."""
+  over the RHS evaluations and comes back here ONCE per training step.  Forward: always the native kernel.  Backward:
+  the fused configuration (scaled_dot, softmax, norm idx 0) runs grand_attention_weights_backward + the dense tails;
+  every other scorer / normaliser differentiates the torch restatement of the layer at x0 (attention_autograd.py)."""
 
   @staticmethod
-  def forward(ctx, x0, wq, bq, wk, bk, layer, eng):
+  def forward(ctx, x0, layer, eng, edge_index, *params):
     x0 = x0.contiguous()
     spec = layer.spec(eng)
-    if not spec.fused:
-      raise NotImplementedError('grand_b200 backward through frozen attention is built for attention_type=scaled_dot, '
-                                'softmax, attention_norm_idx=0')
     att, _, mean_csr = eng.attention_weights(spec, x0, want_attention=True, want_prods=False, want_mean_csr=True)
-    ctx.layer, ctx.engine = layer, eng
-    ctx.save_for_backward(x0, wq, wk)
+    ctx.layer, ctx.engine, ctx.fused, ctx.edge_index = layer, eng, bool(spec.fused), edge_index
+    ctx.names = [n for n, _ in layer.named_parameters()]
+    ctx.save_for_backward(x0, *params)
     ctx.mark_non_differentiable(att)
     return att, mean_csr
 
   @staticmethod
   def backward(ctx, _g_att, c_csr):
-    x0, wq, wk = ctx.saved_tensors
-    eng = ctx.engine
-    dq, dk = eng.attention_weights_backward(ctx.layer.spec(eng), x0, c_csr)
-    gx = dq @ wq + dk @ wk
-    return gx, dq.t() @ x0, dq.sum(0), dk.t() @ x0, dk.sum(0), None, None
+    x0, *params = ctx.saved_tensors
+    eng, layer = ctx.engine, ctx.layer
+    by_name = dict(zip(ctx.names, params))
+    grads = {n: None for n in ctx.names}
+    if ctx.fused and x0.shape[1] % 4 == 0:
+      wq, wk = by_name['Q.weight'], by_name['K.weight']
+      dq, dk = eng.attention_weights_backward(layer.spec(eng), x0, c_csr)
+      gx = dq @ wq + dk @ wk
+      grads.update({'Q.weight': dq.t() @ x0, 'Q.bias': dq.sum(0), 'K.weight': dk.t() @ x0, 'K.bias': dk.sum(0)})
+    else:
+      from .attention_autograd import mean_attention
+      with torch.enable_grad():
+        x0_ = x0.detach().requires_grad_(True)
+        mean = mean_attention(x0_, ctx.edge_index, layer, eng.plan.n_rows)       # caller order, live parameters
+        wanted = [(n, p) for n, p in layer.named_parameters() if p.requires_grad]
+        # c is indexed by CSR position: bring it to the caller's edge order
+        c_caller = torch.zeros_like(mean).index_copy_(0, eng.plan.eid_long, c_csr.contiguous())
+        out = torch.autograd.grad(mean, [x0_] + [p for _, p in wanted], c_caller, allow_unused=True)
+      gx = out[0]
+      for (n, _), g in zip(wanted, out[1:]):
+        grads[n] = g
+    return (gx, None, None, None) + tuple(grads[n] for n in ctx.names)
 
 
 class FrozenLaplacianRhsFn(torch.autograd.Function):

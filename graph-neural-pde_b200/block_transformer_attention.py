@@ -35,7 +35,7 @@ class AttODEblock(ODEblock):
     if not hasattr(layer, 'Q'):
       raise NotImplementedError('grand_b200 backward: the beltrami exp_kernel layer is forward-only')
     eng = self.odefunc.engine(x)
-    frozen, mean_csr = FrozenAttentionFn.apply(x, layer.Q.weight, layer.Q.bias, layer.K.weight, layer.K.bias, layer, eng)
+    frozen, mean_csr = FrozenAttentionFn.apply(x, layer, eng, self.odefunc.edge_index, *layer.parameters())
     eng_t = _transposed_engine(self.odefunc, x)
     self.odefunc.frozen_weights = (mean_csr, eng_t.edge_values_to_csr(frozen))
     return frozen

@@ -191,11 +191,8 @@ int launch_project_qk(const float* x, int n_rows, int n_cols, int d, const float
   GRAND_REQUIRE(smem <= 227 * 1024, GRAND_EUNSUPPORTED,
                 "project_qk: [2*%d, %d] weights + row tile need %zu B of shared memory (> 227 KiB)", ad, d, smem);
   auto kern = project_qk_kernel<RT, OT>;
-  static size_t configured = 0;
-  if (smem > configured) {
-    GRAND_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
-  }
+  // per device and cheap: set on every launch (no process-wide "already done" flag)
+  GRAND_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = (int)((227 * 1024) / (smem + 1024));
   if (per_sm < 1) per_sm = 1;
   if (per_sm > 6) per_sm = 6;

@@ -332,11 +332,8 @@ int launch_project_qk_mma(const float* x, int n_rows, int n_cols, int d, const f
 #define GRAND_LAUNCH_DIRECT(NTV)                                                                                    \
   {                                                                                                                 \
     auto kern = project_qk_mma_direct_kernel<NTV>;                                                                  \
-    static size_t configured = 0;                                                                                   \
-    if (smem_d > configured) {                                                                                      \
-      GRAND_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_d));          \
-      configured = smem_d;                                                                                          \
-    }                                                                                                               \
+    /* per device and cheap: set on every launch (no process-wide "already done" flag) */                           \
+    GRAND_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_d));            \
     kern<<<grid_d, kDirThreads, smem_d, stream>>>(x, n_rows, n_cols, d, d16, ldd, wq, bq, wk, bk, ad, n_tiles_d, q, \
                                                   k);                                                               \
   }
@@ -370,11 +367,7 @@ int launch_project_qk_mma(const float* x, int n_rows, int n_cols, int d, const f
 #define GRAND_LAUNCH_MMA(NTV)                                                                                       \
   {                                                                                                                 \
     auto kern = project_qk_mma_kernel<NTV>;                                                                         \
-    static size_t configured = 0;                                                                                   \
-    if (smem > configured) {                                                                                        \
-      GRAND_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));            \
-      configured = smem;                                                                                            \
-    }                                                                                                               \
+    GRAND_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));              \
     kern<<<grid, kMmaThreads, smem, stream>>>(x, n_rows, n_cols, d, d8, ld, wq, bq, wk, bk, ad, n_tiles, q, k);     \
   }
   switch (nt) {

@@ -105,12 +105,9 @@ def training_blockers(opt):
   """Reasons why `opt` cannot be TRAINED on this engine (forward / evaluation of every one of them runs): checked before
   the first epoch so that an unsupported configuration fails at start-up with one message, not mid-epoch."""
   why = []
-  if opt['block'] == 'attention' and not opt.get('adjoint') and (
-      opt['attention_type'] != 'scaled_dot' or opt['square_plus'] or opt['attention_norm_idx'] != 0
-      or opt['hidden_dim'] % 4 != 0):
-    why.append("block='attention': gradients through the attention frozen at x(0) (reference "
-               "src/block_transformer_attention.py:36-39) are built for attention_type=scaled_dot, softmax, "
-               "attention_norm_idx=0, hidden_dim % 4 == 0")
+  if opt['block'] == 'attention' and not opt.get('adjoint') and opt.get('beltrami') and opt['attention_type'] == 'exp_kernel':
+    why.append("block='attention' with the beltrami exp_kernel layer: gradients through the attention frozen at x(0) "
+               "(reference src/block_transformer_attention.py:36-39) are built for the Q / K layers only")
   if opt['function'] == 'GAT':
     why.append("function='GAT': the GAT scorer is forward-only")
   if opt['function'] == 'transformer' and (opt['attention_type'] != 'scaled_dot' or opt['square_plus']

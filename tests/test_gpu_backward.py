@@ -174,6 +174,65 @@ def test_attention_block_backward_vs_oracle_autograd(method, max_degree):
                      ['x'] + ATT_NAMES)
 
 
+@pytest.mark.parametrize('attention_type,square_plus,norm_idx,reweight', [
+  ('scaled_dot', True, 1, False),      # the reference's tuned Cora configuration (src/best_params.py)
+  ('exp_kernel', True, 1, False),      # ... Citeseer
+  ('cosine_sim', True, 0, False),      # ... Pubmed's scorer
+  ('pearson', False, 1, True),
+])
+def test_attention_block_backward_general_configurations(attention_type, square_plus, norm_idx, reweight):
+  """Gradients through the attention frozen at x(0) for the scorers / normalisers the fused backward kernel does not
+  cover: forward native, the once-per-step attention backward through attention_autograd.mean_attention, the
+  per-evaluation Laplacian backward native.  Against fp64 autograd through the oracle."""
+  from graph_neural_pde_b200.block_transformer_attention import AttODEblock
+  n, d, ad, heads = 300, 32, 16, 4
+  edge_index = make_graph(n, 6 * n, max_degree=150, seed=21)
+  torch.manual_seed(22)
+  x = torch.randn(n, d)
+  opt = default_opt(function='laplacian', block='attention', hidden_dim=d, attention_dim=ad, heads=heads, method='rk4',
+                    step_size=0.5, time=1.0, add_source=True, adjoint=False, attention_type=attention_type,
+                    square_plus=square_plus, attention_norm_idx=norm_idx, reweight_attention=reweight)
+  data = Data(x=x, edge_index=edge_index, edge_attr=None, num_nodes=n)
+  block = AttODEblock(LaplacianODEFunc, (), opt, data, DEV, t=torch.tensor([0, opt['time']])).to(DEV)
+  g = torch.Generator().manual_seed(23)
+  with torch.no_grad():
+    for name, p_ in block.multihead_att_layer.named_parameters():
+      if p_.dim() == 2:
+        p_.copy_((1.5 * torch.randn(p_.shape, generator=g) / p_.shape[1] ** 0.5).to(DEV))
+      elif name == 'output_var':
+        p_.fill_(1.2)
+      elif name == 'lengthscale':
+        p_.fill_(1.7)
+      else:
+        p_.copy_((0.3 * torch.randn(p_.shape, generator=g)).to(DEV))
+    block.odefunc.alpha_train.fill_(0.3)
+    block.odefunc.beta_train.fill_(-0.4)
+  block.train()
+  xd = x.to(DEV).requires_grad_(True)
+  block.set_x0(x.to(DEV))
+  torch.manual_seed(3)
+  w = torch.randn(n, d)
+  z = block(xd)
+  (z * w.to(DEV)).sum().backward()
+  sd = _oracle_params(block)
+  xo = x.double().requires_grad_(True)
+  ei, ew = O.constant_block_graph(edge_index, None, n, {**opt, 'data_norm': 'rw'}, torch.float64)
+  att, _ = O.attention_forward(xo, ei, C.sub_state(sd, 'multihead_att_layer.'), opt, ew)
+  wts = O.laplacian_weights(opt, ew, att)
+  fo = lambda t, y: O.laplacian_rhs(y, ei, wts, opt, sd['odefunc.alpha_train'], sd['odefunc.beta_train'], x.double())
+  zo = O.block_forward(fo, xo, opt['time'], opt)
+  (zo * w.double()).sum().backward()
+  C.assert_close(z, zo, C.RTOL, 'z')
+  names = list(ATT_NAMES)
+  if attention_type == 'exp_kernel':
+    names += ['multihead_att_layer.output_var', 'multihead_att_layer.lengthscale']
+  got = dict(block.named_parameters())
+  for k in names:
+    assert got[k].grad is not None, k
+  assert_grads_close([xd.grad] + [got[k].grad for k in names], [xo.grad] + [sd[k].grad for k in names], GTOL,
+                     ['x'] + names)
+
+
 def test_run_gnn_trains_attention_block(capsys):
   """run_GNN.main with --block attention --function laplacian (the paper's GRAND-l) trains: the start-up check lets
   it through and the loss falls."""
