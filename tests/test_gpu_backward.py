@@ -248,6 +248,22 @@ def test_run_gnn_trains_attention_block(capsys):
   assert len(losses) == 5 and losses[-1] < losses[0], losses
 
 
+def test_run_gnn_trains_the_reference_cora_configuration(capsys):
+  """The reference's tuned Cora configuration (src/best_params.py through `--best_params reference`; `--block attention`
+  given explicitly, as its CLI default would otherwise override the block): GRAND-l with the attention frozen at x(0),
+  scaled_dot + squareplus over attention_norm_idx 1, dopri5 to T = 18.3 without the adjoint, early-stopping model.
+  Trains on the synthetic Cora stand-in: finite losses that fall."""
+  from graph_neural_pde_b200 import run_GNN
+  args = run_GNN.build_parser().parse_args(['--dataset', 'Cora', '--best_params', 'reference', '--block', 'attention',
+                                            '--epoch', '6', '--quiet'])
+  torch.manual_seed(0)
+  run_GNN.main(vars(args))
+  out = capsys.readouterr().out
+  losses = [float(line.split('Loss ')[1].split(',')[0]) for line in out.splitlines() if line.startswith('Epoch:')]
+  assert len(losses) == 5 and all(l == l and abs(l) < 1e6 for l in losses), losses
+  assert min(losses[1:]) < losses[0], losses
+
+
 def test_run_gnn_trains_end_to_end(capsys):
   """The reference's entry point (run_GNN.main) on the synthetic Cora stand-in: a few epochs of GRAND-nl with the
   default early-stopping model; the loss must fall and the attribute chain main() reads must be alive."""
