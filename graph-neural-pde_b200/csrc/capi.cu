@@ -3,11 +3,22 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace grand {
 
 static thread_local char g_error[512] = "";
+bool pdl_enabled() {
+  static int v = -1;                    // GRAND_PDL=0: measurement switch, read once
+  if (v < 0) {
+    const char* e = getenv("GRAND_PDL");
+    v = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
+
 static int64_t g_launches = 0;   // diagnostic counter only (grand_launch_count); updated atomically
 
 void count_launch(int n) { __atomic_fetch_add(&g_launches, (int64_t)n, __ATOMIC_RELAXED); }

@@ -40,6 +40,34 @@ inline int num_sms() {
   return n;
 }
 
+// ---- programmatic dependent launch (PDL) -------------------------------------------------------------------------------------
+// The kernels of one RHS evaluation (projection -> long-row statistics -> edge kernel -> next projection ...) are launched
+// with cudaLaunchAttributeProgrammaticStreamSerialization: a kernel calls pdl_launch_dependents() at its start, so its
+// successor may be scheduled while this one still runs (on the SMs its persistent blocks have already left), and the
+// successor runs its prologue -- barrier / TMEM set-up, weight staging, first work-list fetch -- before pdl_wait(), which
+// returns once the predecessor grid has completed and its memory is visible.  NOTHING a predecessor writes (or still
+// reads while this kernel would overwrite it) may be touched before pdl_wait().  Without the launch attribute both calls
+// are no-ops.  GRAND_PDL=0 launches the plain way (A/B).
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+bool pdl_enabled();
+
+template <class... KArgs, class... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 __device__ __forceinline__ float warp_max(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(kFull, v, o));

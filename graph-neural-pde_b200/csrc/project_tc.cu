@@ -388,6 +388,7 @@ linear_tm_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
   float* bias = reinterpret_cast<float*>(tmem_ptr + 4);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  pdl_launch_dependents();
   if (tid == 0) {
     for (int s = 0; s < P.raw_slots; ++s) {
       tc_mbar_init(tc_smem_u32(full + s), 1);
@@ -434,6 +435,9 @@ linear_tm_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
   const int first_tile = blockIdx.x, tile_step = gridDim.x;
+  // everything above (barriers, tensor memory, bias, split weights) is independent of the previous kernel in the stream;
+  // X is read and Y written only below
+  pdl_wait();
 
   if (warp == 0) {
     // ===== TMA producer =====
@@ -655,8 +659,7 @@ int launch_linear_tc(const float* x, int n_x_rows, int d, const float* w0, const
       P.raw_slots = raw;
       const size_t smem_tm = w_bytes + (size_t)raw * kTcTileBytes + tail_tm;
       GRAND_CUDA_OK(cudaFuncSetAttribute(linear_tm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tm));
-      linear_tm_kernel<<<grid, kTmThreads, smem_tm, stream>>>(xmap, P);
-      GRAND_CUDA_OK(cudaGetLastError());
+      GRAND_CUDA_OK(launch_pdl(linear_tm_kernel, dim3(grid), dim3(kTmThreads), smem_tm, stream, xmap, P));
       count_launch();
       return GRAND_OK;
     }

@@ -269,10 +269,12 @@ __global__ void GRAND_RING_BOUNDS rhs_ring_kernel(const __grid_constant__ RhsArg
     }
   };
 
+  pdl_launch_dependents();
   int u = grab();
   int4 h4 = make_int4(0, 0, 0, 0);
   int2 rec = make_int2(0, 0);
-  fetch(u, h4, rec);
+  fetch(u, h4, rec);                       // the work list is not written by any kernel of the evaluation
+  pdl_wait();                              // Q / K / statistics of this evaluation, and the previous stage's rows, are complete
   while (u < n_seg) {                      // medium rows and long-row segments come first in the list
     const int un = grab();
     int4 h4n = make_int4(0, 0, 0, 0);
@@ -312,8 +314,7 @@ static int launch_ring_inst(const RhsArgs& A, cudaStream_t stream) {
   // per device and cheap: set on every launch (no process-wide "already done" flag)
   GRAND_CUDA_OK(cudaFuncSetAttribute(rhs_ring_kernel<MODE, FULL, HM>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   GRAND_CUDA_OK(cudaFuncSetAttribute(rhs_ring_kernel<MODE, FULL, HM>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-  rhs_ring_kernel<MODE, FULL, HM><<<grid, kRingThreads, smem, stream>>>(A);
-  GRAND_CUDA_OK(cudaGetLastError());
+  GRAND_CUDA_OK(launch_pdl(rhs_ring_kernel<MODE, FULL, HM>, dim3(grid), dim3(kRingThreads), (size_t)smem, stream, A));
   count_launch();
   return GRAND_OK;
 }

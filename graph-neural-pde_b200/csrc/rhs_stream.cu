@@ -107,7 +107,9 @@ lseg_stats_kernel(GraphView g, AttnView a, const float* __restrict__ q, const fl
   __shared__ float sm[kStatsThreads / kWarp][GRAND_MAX_HEADS];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int unit = blockIdx.x;
+  pdl_launch_dependents();
   const int4 desc = __ldg(g.seg_desc + unit);
+  pdl_wait();                              // Q / K come from the projection launched just before
   const int row = desc.x, beg = desc.y, cnt = desc.z;
   const int H = a.heads;
   const bool vec4 = ((a.dk & 3) == 0) && ((a.ad_eff & 3) == 0);
@@ -677,10 +679,12 @@ rhs_stream_kernel(const __grid_constant__ RhsArgs A) {
   };
 
   NoRing no_ring;
+  pdl_launch_dependents();
   int u = grab();
   int4 h4 = make_int4(0, 0, 0, 0);
   int2 rec = make_int2(0, 0);
   fetch(u, h4, rec);
+  pdl_wait();
   while (u < n_units) {
     const int un = grab();
     int4 h4n = make_int4(0, 0, 0, 0);
@@ -703,8 +707,10 @@ static int launch_stream_inst(const RhsArgs& A, cudaStream_t stream) {
   int grid = (n_units + kStreamWarps - 1) / kStreamWarps;
   const int cap = num_sms() * (R == 1 ? GRAND_STREAM_MINBLOCKS : 1);
   if (grid > cap) grid = cap;
-  if (MODE == MODE_FUSED && A.a.heads > 4) rhs_stream_kernel<MODE, FULL, R, GRAND_MAX_HEADS><<<grid, kStreamThreads, 0, stream>>>(A);
-  else rhs_stream_kernel<MODE, FULL, R, 4><<<grid, kStreamThreads, 0, stream>>>(A);
+  if (MODE == MODE_FUSED && A.a.heads > 4)
+    GRAND_CUDA_OK(launch_pdl(rhs_stream_kernel<MODE, FULL, R, GRAND_MAX_HEADS>, dim3(grid), dim3(kStreamThreads), 0, stream, A));
+  else
+    GRAND_CUDA_OK(launch_pdl(rhs_stream_kernel<MODE, FULL, R, 4>, dim3(grid), dim3(kStreamThreads), 0, stream, A));
   GRAND_CUDA_OK(cudaGetLastError());
   count_launch();
   return GRAND_OK;
@@ -743,7 +749,8 @@ int launch_stream_mode(int mode, const RhsArgs& A, cudaStream_t stream) {
   if (mode == MODE_FUSED) {
     if (A.g.n_lunits > 0) {
       GRAND_REQUIRE(A.lrow_stats != nullptr, GRAND_EINVAL, "graph has long rows: workspace lrow_stats is null");
-      lseg_stats_kernel<<<A.g.n_lunits, kStatsThreads, 0, stream>>>(A.g, A.a, A.q, A.k, A.lrow_stats);
+      GRAND_CUDA_OK(launch_pdl(lseg_stats_kernel, dim3(A.g.n_lunits), dim3(kStatsThreads), 0, stream, A.g, A.a, A.q, A.k,
+                               A.lrow_stats));
       GRAND_CUDA_OK(cudaGetLastError());
       count_launch();
     }

@@ -1,15 +1,16 @@
 set -u
 cd /root/repo
-O=gpurun_out
-TAG=${1:-r02p}
-NG=${2:-8}
-timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port 29511 tests/multi_gpu_check.py 2>&1 | grep -E "MULTI_GPU_CHECK|Error|error" | head -5
-timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus $NG --steps 10 --warmup 3 > $O/${TAG}_bench_n${NG}.json 2> $O/${TAG}_bench_n${NG}.err || tail -5 $O/${TAG}_bench_n${NG}.err
-python - "$O/${TAG}_bench_n${NG}.json" <<'PY'
+O=gpurun_out; mkdir -p $O
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+for v in 1 0; do
+GRAND_PDL=$v timeout 200 python bench.py --skip-cpu --no-others --repeats 3 2>/dev/null > $O/r02p_bench_short_pdl$v.json
+python - $v <<'PY'
 import json, sys
-try:
-    d = json.load(open(sys.argv[1]))
-    print('N=%d %s ms/step %.3f us/eval %.1f e2e %.3f parity %.2e phases %s halo %s nvlink floor %.1f' % (d['n_gpus'], d['transport'], d['ms_per_step'], d['us_per_rhs_eval'], d['e2e']['ms_per_step'], d['parity_max_err'], {k: round(v, 1) for k, v in d['phases_per_rhs_eval'].items()}, d['partition']['halo_fraction_of_graph_per_rank'], d['roofline']['nvlink_time_floor_us_per_eval']))
-except Exception as e:
-    print('FAILED', e)
+d = json.load(open('gpurun_out/r02p_bench_short_pdl%s.json' % sys.argv[1])); r = d['roofline']
+print('GRAND_PDL=%s' % sys.argv[1], 'ms/step %.3f (%s) e2e %.3f edge_us %.1f proj_us %.1f' % (d['ms_per_step'], [round(v,3) for v in d['timing']['ms_per_step_repeats']], d['e2e']['ms_per_step'], r['us_per_launch'], r['projection_us_per_launch']))
 PY
+done | tee $O/r02p_pdl.txt
+for w in Cora Photo; do for v in 1 0; do
+GRAND_PDL=$v timeout 100 python bench.py --workload $w --steps 10 --skip-cpu --no-others --repeats 3 2>/dev/null | python -c "
+import json,sys; d=json.loads(sys.stdin.read()); print('$w GRAND_PDL=$v: ms/step %.3f us/eval %.1f'%(d['ms_per_step'],d['us_per_rhs_eval']))"
+done; done | tee -a $O/r02p_pdl.txt
