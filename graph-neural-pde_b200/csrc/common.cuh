@@ -47,7 +47,7 @@ inline int num_sms() {
 // successor runs its prologue -- barrier / TMEM set-up, weight staging, first work-list fetch -- before pdl_wait(), which
 // returns once the predecessor grid has completed and its memory is visible.  NOTHING a predecessor writes (or still
 // reads while this kernel would overwrite it) may be touched before pdl_wait().  Without the launch attribute both calls
-// are no-ops.  GRAND_PDL=0 launches the plain way (A/B).
+// are no-ops.  Measured slower than plain launches (profiles/r02p_pdl.txt): off unless GRAND_PDL=1.
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
