@@ -66,3 +66,17 @@ def mean_attention(x, edge, layer, num_nodes):
   index = edge[int(opt['attention_norm_idx'])]
   att = _squareplus(prods, index, num_nodes) if opt['square_plus'] else _segment_softmax(prods, index, num_nodes)
   return att.mean(dim=1)
+
+
+def transformer_rhs(x, func, x0):
+  """ODEFuncTransformerAtt.forward (reference src/function_transformer_attention.py:38-53) in torch ops, differentiable:
+  f = alpha (A(x) x - x) + beta x0 with A the head-mean attention.  Materialises [E, d] (as the reference's spmm backward
+  does): meant for the graphs the unfused configurations are used on, not for ogbn-arxiv."""
+  layer, edge = func.multihead_att_layer, func.edge_index
+  mean = mean_attention(x, edge, layer, x.shape[0])
+  ax = torch.zeros_like(x).index_add_(0, edge[0], x[edge[1]] * mean.unsqueeze(1))     # torch_sparse.spmm (:35)
+  alpha = func.alpha_train if func.opt['no_alpha_sigmoid'] else torch.sigmoid(func.alpha_train)
+  f = alpha * (ax - x)
+  if func.opt['add_source']:
+    f = f + func.beta_train * x0
+  return f

@@ -10,7 +10,7 @@ import torch
 from torch import nn
 
 from . import _native as N
-from .autograd_rhs import TransformerRhsFn, needs_grad
+from .autograd_rhs import TransformerRhsFn, TransformerRhsGeneralFn, needs_grad
 from .base_classes import ODEFunc
 from .engine import AttentionSpec, RhsEngine
 from .graph_plan import GraphPlan
@@ -170,8 +170,10 @@ class ODEFuncTransformerAtt(ODEFunc):
       layer = self.multihead_att_layer
       if not hasattr(layer, 'Q'):
         raise NotImplementedError('grand_b200 backward: the beltrami exp_kernel layer is forward-only')
-      return TransformerRhsFn.apply(x, layer.Q.weight, layer.Q.bias, layer.K.weight, layer.K.bias, self.alpha_train,
-                                    self.beta_train, self)
+      if layer.spec(self.engine(x)).fused and x.shape[1] % 4 == 0:
+        return TransformerRhsFn.apply(x, layer.Q.weight, layer.Q.bias, layer.K.weight, layer.K.bias, self.alpha_train,
+                                      self.beta_train, self)
+      return TransformerRhsGeneralFn.apply(x, self.alpha_train, self.beta_train, self, *layer.parameters())
     x = x.contiguous()
     engine = self.engine(x)
     f = torch.empty_like(x)

@@ -110,11 +110,10 @@ def training_blockers(opt):
                "(reference src/block_transformer_attention.py:36-39) are built for the Q / K layers only")
   if opt['function'] == 'GAT':
     why.append("function='GAT': the GAT scorer is forward-only")
-  if opt['function'] == 'transformer' and (opt['attention_type'] != 'scaled_dot' or opt['square_plus']
-                                          or opt['attention_norm_idx'] != 0):
-    why.append('transformer backward is built for attention_type=scaled_dot, softmax, attention_norm_idx=0')
-  if opt['function'] == 'transformer' and opt['hidden_dim'] % 4 != 0:
-    why.append('transformer backward needs hidden_dim %% 4 == 0 (got %d)' % opt['hidden_dim'])
+  if opt['function'] == 'transformer' and opt.get('beltrami') and opt['attention_type'] == 'exp_kernel':
+    why.append("function='transformer' with the beltrami exp_kernel layer (Qx / Qp): backward is built for the Q / K layers")
+  if opt['function'] == 'transformer' and opt.get('mix_features'):
+    why.append("function='transformer' with mix_features: the reference itself cannot run it")
   if opt.get('adjoint') and opt.get('adjoint_method') not in ('euler', 'midpoint', 'rk4', 'dopri5', 'adaptive_heun',
                                                               'bosh3'):
     why.append('adjoint_method=%r: built are euler, midpoint, rk4, dopri5, adaptive_heun, bosh3' % opt.get('adjoint_method'))
