@@ -35,6 +35,7 @@ int64_t grand_plan_pack_rows(const int64_t* deg, int64_t n_rows, int32_t tile, i
 }  // extern "C"
 
 #include <algorithm>
+#include <memory>
 #include <new>
 #include <thread>
 #include <vector>
@@ -49,7 +50,8 @@ struct grand_plan_host {
   grand_graph counts;                       // scalar fields; pointer fields stay null (grand_plan_bind fills a copy)
   int32_t max_degree, seg_edges;
   int64_t off[GRAND_PLAN_ARRAYS], cnt[GRAND_PLAN_ARRAYS];
-  std::vector<int32_t> image;               // all arrays back to back, every start a multiple of 16 bytes
+  std::unique_ptr<int32_t[]> image;         // all arrays back to back, every start a multiple of 16 bytes; allocated
+  int64_t image_elems;                      // uninitialised and written exactly once (no zero-fill pass, no staging copies)
 };
 
 namespace {
@@ -75,35 +77,44 @@ void parallel_for(int64_t n, F body) {
   for (auto& th : pool) th.join();
 }
 
-// ptr[k] = first output position of key k, order[p] = input index at output position p; equal keys keep their input order
-template <class Key>
-void stable_counting_sort(int64_t n, int32_t n_keys, Key key, std::vector<int32_t>& ptr, std::vector<int32_t>& order) {
-  const int T = plan_threads(n);
-  std::vector<std::vector<int32_t>> hist(T, std::vector<int32_t>((size_t)n_keys + 1, 0));
-  auto chunk = [&](int t, int64_t& lo, int64_t& hi) { lo = n * t / T; hi = n * (t + 1) / T; };
-  {
+// Stable counting sort in two steps, each split over a few host threads (per-thread histograms over contiguous chunks
+// of the input keep equal keys in input order).  count(): ptr[k] = first output position of key k (ptr has n_keys + 1
+// entries).  scatter(): order[p] = input index at output position p.  Between the two the caller can size its outputs.
+struct CountingSort {
+  int T = 1;
+  int64_t n = 0;
+  int32_t n_keys = 0;
+  std::vector<std::vector<int32_t>> hist;
+
+  void chunk(int t, int64_t& lo, int64_t& hi) const { lo = n * t / T; hi = n * (t + 1) / T; }
+
+  template <class Key>
+  void count(int64_t n_, int32_t n_keys_, Key key, int32_t* ptr) {
+    n = n_; n_keys = n_keys_; T = plan_threads(n);
+    hist.assign(T, std::vector<int32_t>((size_t)n_keys + 1, 0));
     std::vector<std::thread> pool;
-    auto count = [&](int t) { int64_t lo, hi; chunk(t, lo, hi); for (int64_t i = lo; i < hi; ++i) ++hist[t][key(i)]; };
-    for (int t = 1; t < T; ++t) pool.emplace_back(count, t);
-    count(0);
+    auto body = [&](int t) { int64_t lo, hi; chunk(t, lo, hi); for (int64_t i = lo; i < hi; ++i) ++hist[t][key(i)]; };
+    for (int t = 1; t < T; ++t) pool.emplace_back(body, t);
+    body(0);
     for (auto& th : pool) th.join();
+    int32_t run = 0;
+    for (int32_t k = 0; k < n_keys; ++k) {       // hist[t][k] becomes thread t's first position for key k
+      ptr[k] = run;
+      for (int t = 0; t < T; ++t) { const int32_t c = hist[t][k]; hist[t][k] = run; run += c; }
+    }
+    ptr[n_keys] = run;
   }
-  ptr.assign((size_t)n_keys + 1, 0);
-  int32_t run = 0;
-  for (int32_t k = 0; k < n_keys; ++k) {       // hist[t][k] becomes thread t's first position for key k
-    ptr[k] = run;
-    for (int t = 0; t < T; ++t) { const int32_t c = hist[t][k]; hist[t][k] = run; run += c; }
-  }
-  ptr[n_keys] = run;
-  order.resize((size_t)n);
-  {
+
+  template <class Key>
+  void scatter(Key key, int32_t* order) {
     std::vector<std::thread> pool;
-    auto scatter = [&](int t) { int64_t lo, hi; chunk(t, lo, hi); for (int64_t i = lo; i < hi; ++i) order[hist[t][key(i)]++] = (int32_t)i; };
-    for (int t = 1; t < T; ++t) pool.emplace_back(scatter, t);
-    scatter(0);
+    auto body = [&](int t) { int64_t lo, hi; chunk(t, lo, hi); for (int64_t i = lo; i < hi; ++i) order[hist[t][key(i)]++] = (int32_t)i; };
+    for (int t = 1; t < T; ++t) pool.emplace_back(body, t);
+    body(0);
     for (auto& th : pool) th.join();
+    hist.clear();
   }
-}
+};
 
 }  // namespace
 
@@ -127,39 +138,94 @@ int grand_plan_create(const int64_t* edge_index, int64_t n_edges, int32_t n_rows
 #ifdef GRAND_PLAN_TIMING
     auto tick = std::chrono::steady_clock::now();
 #endif
-    // 1. CSR by edge_index[0], stable (edges of a row keep the caller's relative order), and the CSC view: two counting
-    //    sorts, each split over a few host threads (per-thread histograms over contiguous chunks of the input keep it stable)
+    // 1. validate; row degrees and CSR row pointer (first half of the stable counting sort by edge_index[0])
     for (int64_t e = 0; e < E; ++e)
       GRAND_REQUIRE(row[e] >= 0 && row[e] < n_rows && col[e] >= 0 && col[e] < n_cols, GRAND_EINVAL,
                     "plan_create: edge %lld = (%lld, %lld) out of range [%d, %d)", (long long)e, (long long)row[e],
                     (long long)col[e], n_rows, n_cols);
-    std::vector<int32_t> rowptr, colptr, eid, csc_pos, col_csr(E), erow(E);
-    stable_counting_sort(E, n_rows, [&](int64_t e) { return (int32_t)row[e]; }, rowptr, eid);
-    parallel_for(E, [&](int64_t lo, int64_t hi) {
-      for (int64_t p = lo; p < hi; ++p) { col_csr[p] = (int32_t)col[eid[p]]; erow[p] = (int32_t)row[eid[p]]; }
-    });
-    stable_counting_sort(E, n_cols, [&](int64_t p) { return col_csr[p]; }, colptr, csc_pos);
+    std::vector<int32_t> rowptr_v((size_t)n_rows + 1);
+    CountingSort by_row;
+    by_row.count(E, n_rows, [&](int64_t e) { return (int32_t)row[e]; }, rowptr_v.data());
     std::vector<int64_t> deg(n_rows);
-    for (int32_t r = 0; r < n_rows; ++r) deg[r] = rowptr[r + 1] - rowptr[r];
-    GRAND_PLAN_TICK("csr+csc")
     int64_t max_degree = 0;
-    for (int32_t r = 0; r < n_rows; ++r) max_degree = std::max(max_degree, deg[r]);
+    for (int32_t r = 0; r < n_rows; ++r) { deg[r] = rowptr_v[r + 1] - rowptr_v[r]; max_degree = std::max(max_degree, deg[r]); }
+    GRAND_PLAN_TICK("degrees")
 
-    // 2. tiles: chunks of the rows with more than `tile` edges first (longest rows first), then the packed windows
-    std::vector<int32_t> split_rows;
-    for (int32_t r = 0; r < n_rows; ++r)
+    // 2. everything that only needs the degrees: which rows are cut into chunks (longest first), the packed windows, the
+    //    work list's long / medium rows -> every array size
+    std::vector<int32_t> split_rows, long_rows, med_rows;
+    for (int32_t r = 0; r < n_rows; ++r) {
       if (deg[r] > tile) split_rows.push_back(r);
+      if (deg[r] > seg_edges) long_rows.push_back(r);
+      else if (deg[r] > tile) med_rows.push_back(r);
+    }
     sort_longest_first(split_rows, deg);
-    std::vector<int32_t> split_tile0(split_rows.size() + 1, 0);
+    sort_longest_first(long_rows, deg);
+    sort_longest_first(med_rows, deg);
+    std::vector<int32_t> split_tile0(split_rows.size() + 1, 0), lrow_slot0(long_rows.size() + 1, 0);
     for (size_t i = 0; i < split_rows.size(); ++i)
       split_tile0[i + 1] = split_tile0[i] + (int32_t)((deg[split_rows[i]] + tile - 1) / tile);
-    const int32_t n_split_tiles = split_tile0.back();
+    for (size_t i = 0; i < long_rows.size(); ++i)
+      lrow_slot0[i + 1] = lrow_slot0[i] + (int32_t)((deg[long_rows[i]] + seg_edges - 1) / seg_edges);
+    const int32_t n_split_tiles = split_tile0.back(), n_lunits = lrow_slot0.back();
     std::vector<int64_t> pfirst(std::max<int32_t>(n_rows, 1)), pcount(std::max<int32_t>(n_rows, 1));
     const int64_t n_pack = grand_plan_pack_rows(deg.data(), n_rows, tile, max_rows, pfirst.data(), pcount.data());
     if (n_pack < 0) return (int)n_pack;
     const int64_t n_tiles = (int64_t)n_split_tiles + n_pack;
     GRAND_REQUIRE(n_tiles < ((int64_t)1 << 31) / (2 * tile), GRAND_EUNSUPPORTED, "plan_create: too many windows");
-    std::vector<int32_t> tile_row(n_tiles), tile_beg(n_tiles), tile_nrows(n_tiles), tile_split(n_tiles);
+    GRAND_PLAN_TICK("lists")
+
+    // 3. the image: sizes -> offsets -> ONE uninitialised allocation; every array below is written in place
+    grand_plan_host* P = new (std::nothrow) grand_plan_host();
+    GRAND_REQUIRE(P != nullptr, GRAND_ECUDA, "plan_create: out of host memory");
+    std::unique_ptr<grand_plan_host> guard(P);
+    const int64_t sizes[GRAND_PLAN_ARRAYS] = {
+      (int64_t)n_rows + 1, E, E, E, n_tiles * 4, n_tiles * tile * 2, (int64_t)split_tile0.size(), (int64_t)n_cols + 1, E,
+      ((int64_t)n_lunits + (int64_t)med_rows.size()) * 4, (int64_t)lrow_slot0.size(), (int64_t)long_rows.size(), n_tiles,
+      n_tiles, n_tiles, n_tiles};
+    int64_t total = 0;
+    for (int i = 0; i < GRAND_PLAN_ARRAYS; ++i) {
+      P->off[i] = total;
+      P->cnt[i] = sizes[i];
+      total += (sizes[i] + 3) & ~(int64_t)3;
+    }
+    P->image_elems = std::max<int64_t>(total, 4);
+    P->image.reset(new int32_t[(size_t)P->image_elems]);
+    int32_t* const img = P->image.get();
+    for (int i = 0; i < GRAND_PLAN_ARRAYS; ++i)                    // the <= 3 padding elements behind every array
+      for (int64_t k = P->off[i] + P->cnt[i]; k < (i + 1 < GRAND_PLAN_ARRAYS ? P->off[i + 1] : P->image_elems); ++k) img[k] = 0;
+    int32_t* const rowptr = img + P->off[GRAND_PLAN_ROWPTR];
+    int32_t* const col_csr = img + P->off[GRAND_PLAN_COL];
+    int32_t* const erow = img + P->off[GRAND_PLAN_EROW];
+    int32_t* const eid = img + P->off[GRAND_PLAN_EID];
+    int32_t* const win_hdr = img + P->off[GRAND_PLAN_WIN_HDR];
+    int32_t* const win_rec = img + P->off[GRAND_PLAN_WIN_REC];
+    int32_t* const colptr = img + P->off[GRAND_PLAN_COLPTR];
+    int32_t* const csc_pos = img + P->off[GRAND_PLAN_CSC_POS];
+    int32_t* const seg_desc = img + P->off[GRAND_PLAN_SEG_DESC];
+    int32_t* const tile_row = img + P->off[GRAND_PLAN_TILE_ROW];
+    int32_t* const tile_beg = img + P->off[GRAND_PLAN_TILE_BEG];
+    int32_t* const tile_nrows = img + P->off[GRAND_PLAN_TILE_NROWS];
+    int32_t* const tile_split = img + P->off[GRAND_PLAN_TILE_SPLIT];
+    std::copy(rowptr_v.begin(), rowptr_v.end(), rowptr);
+    std::copy(split_tile0.begin(), split_tile0.end(), img + P->off[GRAND_PLAN_SPLIT_TILE0]);
+    std::copy(lrow_slot0.begin(), lrow_slot0.end(), img + P->off[GRAND_PLAN_LROW_SLOT0]);
+    std::copy(long_rows.begin(), long_rows.end(), img + P->off[GRAND_PLAN_LROW_ROW]);
+
+    // 4. CSR (second half of the sort by row: eid; then columns / rows in CSR order) and the CSC view (sort of the CSR
+    //    positions by column)
+    by_row.scatter([&](int64_t e) { return (int32_t)row[e]; }, eid);
+    parallel_for(E, [&](int64_t lo, int64_t hi) {
+      for (int64_t p = lo; p < hi; ++p) { col_csr[p] = (int32_t)col[eid[p]]; erow[p] = (int32_t)row[eid[p]]; }
+    });
+    {
+      CountingSort by_col;
+      by_col.count(E, n_cols, [&](int64_t p) { return col_csr[p]; }, colptr);
+      by_col.scatter([&](int64_t p) { return col_csr[p]; }, csc_pos);
+    }
+    GRAND_PLAN_TICK("csr+csc")
+
+    // 5. tiles: chunks of the rows with more than `tile` edges first (longest rows first), then the packed windows
     for (size_t i = 0; i < split_rows.size(); ++i) {
       const int32_t r = split_rows[i];
       for (int32_t t = split_tile0[i], k = 0; t < split_tile0[i + 1]; ++t, ++k) {
@@ -170,9 +236,7 @@ int grand_plan_create(const int64_t* edge_index, int64_t n_edges, int32_t n_rows
       const int64_t t = n_split_tiles + w;
       tile_row[t] = (int32_t)pfirst[w]; tile_beg[t] = rowptr[pfirst[w]]; tile_nrows[t] = (int32_t)pcount[w]; tile_split[t] = -1;
     }
-    GRAND_PLAN_TICK("tiles")
-    // 3. window header (int4) and per-lane record (int2), see csrc/edge_common.cuh
-    std::vector<int32_t> win_hdr(n_tiles * 4), win_rec(n_tiles * tile * 2);
+    // window header (int4) and per-lane record (int2), see csrc/edge_common.cuh
     parallel_for(n_tiles, [&](int64_t t_lo, int64_t t_hi) {
     for (int64_t t = t_lo; t < t_hi; ++t) {
       const int32_t r0 = tile_row[t], beg = tile_beg[t], nr = tile_nrows[t];
@@ -205,19 +269,7 @@ int grand_plan_create(const int64_t* edge_index, int64_t n_edges, int32_t n_rows
     }
     });
     GRAND_PLAN_TICK("windows")
-    // 4. work list of the persistent edge kernel: long segments (longest row first), medium rows (longest first)
-    std::vector<int32_t> long_rows, med_rows;
-    for (int32_t r = 0; r < n_rows; ++r) {
-      if (deg[r] > seg_edges) long_rows.push_back(r);
-      else if (deg[r] > tile) med_rows.push_back(r);
-    }
-    sort_longest_first(long_rows, deg);
-    sort_longest_first(med_rows, deg);
-    std::vector<int32_t> lrow_slot0(long_rows.size() + 1, 0);
-    for (size_t i = 0; i < long_rows.size(); ++i)
-      lrow_slot0[i + 1] = lrow_slot0[i] + (int32_t)((deg[long_rows[i]] + seg_edges - 1) / seg_edges);
-    const int32_t n_lunits = lrow_slot0.back();
-    std::vector<int32_t> seg_desc(((size_t)n_lunits + med_rows.size()) * 4);
+    // 6. work list of the persistent edge kernel: long segments (longest row first), medium rows (longest first)
     for (size_t i = 0; i < long_rows.size(); ++i) {
       const int32_t r = long_rows[i];
       for (int32_t u = lrow_slot0[i], k = 0; u < lrow_slot0[i + 1]; ++u, ++k) {
@@ -231,32 +283,13 @@ int grand_plan_create(const int64_t* edge_index, int64_t n_edges, int32_t n_rows
       const int32_t r = med_rows[i];
       seg_desc[4 * u + 0] = r; seg_desc[4 * u + 1] = rowptr[r]; seg_desc[4 * u + 2] = (int32_t)deg[r]; seg_desc[4 * u + 3] = -1;
     }
-
     GRAND_PLAN_TICK("worklist")
-    // 5. pack everything into one image
-    grand_plan_host* P = new (std::nothrow) grand_plan_host();
-    GRAND_REQUIRE(P != nullptr, GRAND_ECUDA, "plan_create: out of host memory");
-    const std::vector<int32_t>* arrays[GRAND_PLAN_ARRAYS] = {
-      &rowptr, &col_csr, &erow, &eid, &win_hdr, &win_rec, &split_tile0, &colptr, &csc_pos, &seg_desc, &lrow_slot0,
-      &long_rows, &tile_row, &tile_beg, &tile_nrows, &tile_split};
-    int64_t total = 0;
-    for (int i = 0; i < GRAND_PLAN_ARRAYS; ++i) {
-      P->off[i] = total;
-      P->cnt[i] = (int64_t)arrays[i]->size();
-      total += (P->cnt[i] + 3) & ~(int64_t)3;
-    }
-    P->image.resize((size_t)std::max<int64_t>(total, 4));
-    for (int i = 0; i < GRAND_PLAN_ARRAYS; ++i) {
-      const int32_t* src = arrays[i]->data();
-      int32_t* dst = P->image.data() + P->off[i];
-      parallel_for(P->cnt[i], [=](int64_t lo, int64_t hi) { std::copy(src + lo, src + hi, dst + lo); });
-    }
     grand_graph& g = P->counts;
     g = grand_graph();
     g.n_rows = n_rows; g.n_cols = n_cols; g.n_edges = (int32_t)E; g.n_tiles = (int32_t)n_tiles;
     g.n_split_rows = (int32_t)split_rows.size(); g.n_split_tiles = n_split_tiles;
     g.n_lunits = n_lunits; g.n_munits = (int32_t)med_rows.size(); g.n_lrows = (int32_t)long_rows.size();
-    GRAND_PLAN_TICK("image")
+    guard.release();
     P->max_degree = (int32_t)max_degree;
     P->seg_edges = seg_edges;
     *out = P;
@@ -272,7 +305,7 @@ int grand_plan_describe(const grand_plan_host* plan, grand_graph* counts, int32_
   if (!plan) return GRAND_EINVAL;
   if (counts) *counts = plan->counts;
   if (max_degree) *max_degree = plan->max_degree;
-  if (image_elems) *image_elems = (int64_t)plan->image.size();
+  if (image_elems) *image_elems = plan->image_elems;
   for (int i = 0; i < GRAND_PLAN_ARRAYS; ++i) {
     if (offsets) offsets[i] = plan->off[i];
     if (elems) elems[i] = plan->cnt[i];
@@ -280,7 +313,7 @@ int grand_plan_describe(const grand_plan_host* plan, grand_graph* counts, int32_
   return GRAND_OK;
 }
 
-const int32_t* grand_plan_image(const grand_plan_host* plan) { return plan ? plan->image.data() : nullptr; }
+const int32_t* grand_plan_image(const grand_plan_host* plan) { return plan ? plan->image.get() : nullptr; }
 
 int grand_plan_bind(const grand_plan_host* plan, const int32_t* image, grand_graph* g) {
   if (!plan || !image || !g) return GRAND_EINVAL;

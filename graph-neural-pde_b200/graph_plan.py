@@ -82,10 +82,11 @@ class GraphPlan:
       N.check(lib.grand_plan_describe(handle, C.byref(counts), C.byref(max_degree), C.byref(image_elems), offsets, elems))
       host = np.ctypeslib.as_array(C.cast(lib.grand_plan_image(handle), C.POINTER(C.c_int32)),
                                    shape=(int(image_elems.value),))
-      image = torch.from_numpy(host.copy())
+      # ONE transfer, straight from the library's buffer (a synchronous copy: the buffer may be freed right after); every
+      # array below is a view into the device image.  A host-side plan (tests) takes its own copy instead.
+      self.image = torch.from_numpy(host).to(device) if device.type != 'cpu' else torch.from_numpy(host.copy())
     finally:
       lib.grand_plan_destroy(handle)
-    self.image = image.to(device)                  # ONE transfer; every array below is a view into it
     for i, name in enumerate(PLAN_ARRAYS):
       view = self.image[int(offsets[i]):int(offsets[i]) + int(elems[i])]
       setattr(self, name, view.view(*_SHAPES[name]) if name in _SHAPES else view)
