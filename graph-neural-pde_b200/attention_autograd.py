@@ -80,3 +80,27 @@ def transformer_rhs(x, func, x0):
   if func.opt['add_source']:
     f = f + func.beta_train * x0
   return f
+
+
+def gat_rhs(x, func, x0):
+  """ODEFuncAtt.forward (reference src/function_GAT_attention.py:31-64, layer :105-116) in torch ops, differentiable:
+  additive scorer LeakyReLU(a . [h_i ; h_j]) per head, segment softmax, then -- by linearity of the per-head spmm's and
+  their mean -- ONE aggregation with the head-mean attention of x (or of x W followed by Wout with mix_features)."""
+  N.require_cuda(x, 'x')
+  layer, edge, opt = func.multihead_att_layer, func.edge_index, func.opt
+  h, dk, n = layer.h, layer.d_k, x.shape[0]
+  wx = torch.mm(x, layer.W)                                                           # :106
+  hh = wx.view(-1, h, dk).transpose(1, 2)                                             # [N, d_k, H]  :107-108
+  edge_h = torch.cat((hh[edge[0]], hh[edge[1]]), dim=1).transpose(0, 1)               # [2 d_k, E, H]  :111-112
+  scores = torch.nn.functional.leaky_relu(torch.sum(layer.a * edge_h, dim=0), layer.alpha)   # :113
+  mean = _segment_softmax(scores, edge[int(opt['attention_norm_idx'])], n).mean(dim=1)        # :114
+  if opt['mix_features']:                                                             # :32-37
+    agg = torch.zeros_like(wx).index_add_(0, edge[0], wx[edge[1]] * mean.unsqueeze(1))
+    ax = torch.mm(agg, layer.Wout)
+  else:                                                                               # :38-42
+    ax = torch.zeros_like(x).index_add_(0, edge[0], x[edge[1]] * mean.unsqueeze(1))
+  alpha = func.alpha_train if opt['no_alpha_sigmoid'] else torch.sigmoid(func.alpha_train)
+  f = alpha * (ax - x)
+  if opt['add_source']:
+    f = f + func.beta_train * x0
+  return f

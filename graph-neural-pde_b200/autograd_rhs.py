@@ -117,21 +117,19 @@ class TransformerRhsFn(torch.autograd.Function):
     return gx, dwq, dbq, dwk, dbk, dalpha, dbeta, None
 
 
-class TransformerRhsGeneralFn(torch.autograd.Function):
-  """f = ODEFuncTransformerAtt.forward(t, x) for the configurations the fused backward kernel does not cover (cosine /
-  pearson / exp-kernel scorers, squareplus, attention_norm_idx 1, reweighting, widths that are not a multiple of 4).
-  Forward: the native general pipeline, as without gradients.  Backward: autograd through the torch restatement of the
-  same evaluation (attention_autograd.transformer_rhs) -- edge-sized torch kernels per evaluation, the price of a
+class GeneralRhsFn(torch.autograd.Function):
+  """One RHS evaluation of a function WITHOUT a fused backward kernel as an autograd node: the transformer function in
+  the configurations outside scaled_dot / softmax / norm idx 0 / width % 4 == 0 (cosine, pearson, exp kernel, squareplus,
+  idx 1, reweighting), and the GAT function (incl. mix_features).  Forward: the function's native evaluation
+  (`func.native_forward`), as without gradients.  Backward: autograd through the torch restatement of the same
+  evaluation (`func.torch_rhs`, attention_autograd.py) -- edge-sized torch kernels per evaluation, the price of a
   configuration outside the fused path; the reference pays it for every configuration."""
 
   @staticmethod
   def forward(ctx, x, alpha_train, beta_train, func, *layer_params):
     x = x.contiguous()
-    eng = func.engine(x)
-    f = torch.empty_like(x)
-    ep = func.residual_epilogue(eng, func.stage_x0(eng), f_out=f)
-    eng.rhs_attention(func.multihead_att_layer.spec(eng), x, ep)
-    ctx.func, ctx.engine = func, eng
+    f = func.native_forward(x)
+    ctx.func, ctx.engine = func, func.engine(x)
     ctx.x0 = func.x0 if func.opt['add_source'] else None
     ctx.n_layer = len(layer_params)
     ctx.save_for_backward(x)
@@ -139,7 +137,6 @@ class TransformerRhsGeneralFn(torch.autograd.Function):
 
   @staticmethod
   def backward(ctx, g):
-    from .attention_autograd import transformer_rhs
     (x,) = ctx.saved_tensors
     func = ctx.func
     _same_engine(ctx, func, x)
@@ -147,12 +144,15 @@ class TransformerRhsGeneralFn(torch.autograd.Function):
     assert len(layer_params) == ctx.n_layer
     with torch.enable_grad():
       x_ = x.detach().requires_grad_(True)
-      f_ = transformer_rhs(x_, func, ctx.x0)
+      f_ = func.torch_rhs(x_, ctx.x0)
       wanted = [x_, func.alpha_train, func.beta_train] + layer_params
       live = [w for w in wanted if w.requires_grad]
       got = iter(torch.autograd.grad(f_, live, g.contiguous(), allow_unused=True))
     grads = [next(got) if w.requires_grad else None for w in wanted]
     return (grads[0], grads[1], grads[2], None) + tuple(grads[3:])
+
+
+TransformerRhsGeneralFn = GeneralRhsFn
 
 
 class LaplacianRhsFn(torch.autograd.Function):

@@ -131,8 +131,12 @@ class ODEFuncAtt(ODEFunc):
     self._bump_nfe()
     N.require_cuda(x, 'x')
     if needs_grad(self, x):
-      raise NotImplementedError('grand_b200 backward is built for the transformer (scaled_dot) and Laplacian functions')
-    x = x.contiguous()
+      from .autograd_rhs import GeneralRhsFn
+      return GeneralRhsFn.apply(x, self.alpha_train, self.beta_train, self, *self.multihead_att_layer.parameters())
+    return self.native_forward(x.contiguous())
+
+  def native_forward(self, x):
+    """The evaluation itself on the native library (no autograd graph)."""
     if self.opt['mix_features']:
       return self._mix_features_rhs(x)
     engine = self.engine(x)
@@ -140,6 +144,11 @@ class ODEFuncAtt(ODEFunc):
     engine.rhs_attention(self.multihead_att_layer.spec(engine), x,
                          self.residual_epilogue(engine, self.stage_x0(engine), f_out=f))
     return f
+
+  def torch_rhs(self, x, x0):
+    """Differentiable torch restatement of the same evaluation (the GAT scorer has no backward kernel)."""
+    from .attention_autograd import gat_rhs
+    return gat_rhs(x, self, x0)
 
   def __repr__(self):
     return self.__class__.__name__ + ' (' + str(self.in_features) + ' -> ' + str(self.out_features) + ')'

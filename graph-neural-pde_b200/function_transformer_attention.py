@@ -174,12 +174,20 @@ class ODEFuncTransformerAtt(ODEFunc):
         return TransformerRhsFn.apply(x, layer.Q.weight, layer.Q.bias, layer.K.weight, layer.K.bias, self.alpha_train,
                                       self.beta_train, self)
       return TransformerRhsGeneralFn.apply(x, self.alpha_train, self.beta_train, self, *layer.parameters())
-    x = x.contiguous()
+    return self.native_forward(x.contiguous())
+
+  def native_forward(self, x):
+    """The evaluation itself, one C call (no autograd graph)."""
     engine = self.engine(x)
     f = torch.empty_like(x)
     ep = self.residual_epilogue(engine, self.stage_x0(engine), f_out=f)
     engine.rhs_attention(self.multihead_att_layer.spec(engine), x, ep)
     return f
+
+  def torch_rhs(self, x, x0):
+    """Differentiable torch restatement of the same evaluation (backward of the unfused configurations)."""
+    from .attention_autograd import transformer_rhs
+    return transformer_rhs(x, self, x0)
 
   def __repr__(self):
     return self.__class__.__name__ + ' (' + str(self.in_features) + ' -> ' + str(self.out_features) + ')'

@@ -108,8 +108,6 @@ def training_blockers(opt):
   if opt['block'] == 'attention' and not opt.get('adjoint') and opt.get('beltrami') and opt['attention_type'] == 'exp_kernel':
     why.append("block='attention' with the beltrami exp_kernel layer: gradients through the attention frozen at x(0) "
                "(reference src/block_transformer_attention.py:36-39) are built for the Q / K layers only")
-  if opt['function'] == 'GAT':
-    why.append("function='GAT': the GAT scorer is forward-only")
   if opt['function'] == 'transformer' and opt.get('beltrami') and opt['attention_type'] == 'exp_kernel':
     why.append("function='transformer' with the beltrami exp_kernel layer (Qx / Qp): backward is built for the Q / K layers")
   if opt['function'] == 'transformer' and opt.get('mix_features'):

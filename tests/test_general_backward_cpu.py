@@ -95,3 +95,53 @@ def test_general_transformer_backward_vs_oracle_autograd(monkeypatch, attention_
     assert float((got[k].grad - want.grad).abs().max()) <= 1e-9 * float(want.grad.abs().max() + 1e-30) + 1e-14, k
     checked += 1
   assert checked >= 4
+
+
+@pytest.mark.parametrize('mix_features,norm_idx', [(False, 0), (False, 1), (True, 0)])
+def test_gat_backward_vs_oracle_autograd(monkeypatch, mix_features, norm_idx):
+  """Gradients through the GAT function (reference src/function_GAT_attention.py:31-64), incl. mix_features: native forward
+  stood in for by the oracle, backward = attention_autograd.gat_rhs through autograd_rhs.GeneralRhsFn."""
+  from graph_neural_pde_b200 import function_GAT_attention as FG
+  monkeypatch.setattr(N, 'require_cuda', lambda t, what: None)
+  monkeypatch.setattr(AA.N, 'require_cuda', lambda t, what: None)
+  n, d, ad, h = 60, 12, 16, 4
+  edge_index = make_graph(n, 220, max_degree=25, seed=6)
+  torch.manual_seed(2)
+  x = torch.randn(n, d, dtype=torch.float64)
+  x0 = torch.randn(n, d, dtype=torch.float64)
+  opt = default_opt(function='GAT', block='constant', hidden_dim=d, attention_dim=ad, heads=h, mix_features=mix_features,
+                    attention_norm_idx=norm_idx, add_source=True, self_loop_weight=0, leaky_relu_slope=0.2)
+  data = Data(x=x, edge_index=edge_index, edge_attr=None, num_nodes=n)
+  func = FG.ODEFuncAtt(d, d, opt, data, torch.device('cpu')).double()
+  with torch.no_grad():
+    for p in func.multihead_att_layer.parameters():
+      p.copy_(torch.randn(p.shape, dtype=torch.float64) * 0.4)
+    func.alpha_train.fill_(0.3)
+    func.beta_train.fill_(-0.4)
+  func.x0 = x0
+  func.train()
+
+  def oracle_forward(xx):
+    P = {k: v.detach() for k, v in func.multihead_att_layer.state_dict().items()}
+    with torch.no_grad():
+      return O.gat_rhs(xx, func.edge_index, P, opt, func.alpha_train.detach(), func.beta_train.detach(), x0)
+
+  monkeypatch.setattr(func, 'native_forward', oracle_forward)
+  monkeypatch.setattr(func, 'engine', lambda xx: 'the engine')
+  xg = x.clone().requires_grad_(True)
+  g = torch.randn(n, d, dtype=torch.float64)
+  f = func(torch.tensor(0.0), xg)
+  (f * g).sum().backward()
+  P = {k: v.detach().clone().requires_grad_(True) for k, v in func.multihead_att_layer.state_dict().items()}
+  alpha = func.alpha_train.detach().clone().requires_grad_(True)
+  beta = func.beta_train.detach().clone().requires_grad_(True)
+  xo = x.clone().requires_grad_(True)
+  fo = O.gat_rhs(xo, func.edge_index, P, opt, alpha, beta, x0)
+  assert float((f.detach() - fo.detach()).abs().max()) < 1e-12
+  (fo * g).sum().backward()
+  assert float((xg.grad - xo.grad).abs().max() / xo.grad.abs().max()) < 1e-10
+  assert float((func.alpha_train.grad - alpha.grad).abs().max()) < 1e-10 * float(alpha.grad.abs().max() + 1)
+  got = dict(func.multihead_att_layer.named_parameters())
+  for k in ('W', 'a') + (('Wout',) if mix_features else ()):
+    assert got[k].grad is not None, k
+    assert float((got[k].grad - P[k].grad).abs().max()) <= 1e-9 * float(P[k].grad.abs().max()) + 1e-14, k
