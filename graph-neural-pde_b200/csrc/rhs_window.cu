@@ -34,49 +34,9 @@ constexpr int kRhsWarps = kRhsThreads / kWarp;
 #ifndef GRAND_DIRECT_MINBLOCKS
 #define GRAND_DIRECT_MINBLOCKS 12
 #endif
-// A/B build switches for the next measurements (tools/ab_stage.sh builds and times the variants); the defaults below
-// are the measured-best configuration and compile to exactly the validated kernel:
-//   GRAND_SEGMAX_SHUFFLE=1     segment max by the 11-instruction shuffle reduction instead of redux.sync (ncu: the
-//                              non-uniform-mask redux expands to ~28 instructions per call)
-//   GRAND_EPI_TERMS_BATCH=2    stage-combine terms loaded two at a time (8 instead of 16 registers in the epilogue; the
-//                              40-register build spills there)
-//   GRAND_WINDOW_L2_PREFETCH=0 no L2 prefetch of the window's epilogue rows at window start (~35 instructions per window;
-//                              added when the epilogue loads were the top stall, may no longer pay)
-//   GRAND_PERSISTENT=k         k > 0: at most k x (SMs x resident blocks) blocks are launched and every warp loops over
-//                              its windows (amortises the ~100-instruction per-window prologue; register staging only)
-//   GRAND_GATHER_FIRST=1       the first batch of the window's first row is requested BEFORE the score phase, so its
-//                              latency overlaps the Q / K round trip and the softmax (needs registers: pair it with
-//                              GRAND_DIRECT_MINBLOCKS=8 or 10)
-#ifndef GRAND_GATHER_FIRST
-#define GRAND_GATHER_FIRST 0
-#endif
-#ifndef GRAND_PERSISTENT
-#define GRAND_PERSISTENT 0
-#endif
-#if GRAND_PERSISTENT
-#define GRAND_EXIT_WINDOW continue
-#define GRAND_EXIT_ROWLOOP break
-#else
-#define GRAND_EXIT_WINDOW return
-#define GRAND_EXIT_ROWLOOP return
-#endif
-#ifndef GRAND_WINDOW_L2_PREFETCH
-#define GRAND_WINDOW_L2_PREFETCH 1
-#endif
-#ifndef GRAND_SEGMAX_SHUFFLE
-#define GRAND_SEGMAX_SHUFFLE 0
-#endif
-#if GRAND_SEGMAX_SHUFFLE
-#define GRAND_SEG_MAX(s) seg_max(s, lane, lo, hi)
-#else
-#define GRAND_SEG_MAX(s) seg_max_redux(s, smask)
-#endif
-#ifndef GRAND_EPI_TERMS_BATCH
-#define GRAND_EPI_TERMS_BATCH 4
-#endif
-#ifndef GRAND_EPI_PREFETCH
-#define GRAND_EPI_PREFETCH 0   // measured: 350 us with, 337 us without (the prefetched lines displace gather rows in L1)
-#endif
+// (The A/B build switches of round 1 -- shuffle segment max, two-at-a-time epilogue terms, persistent loop, gather-first,
+// no L2 prefetch, L1 epilogue prefetch -- were measured in round 2 (profiles/r02_edge_ab_runs.txt), none won; they are
+// resolved to the validated defaults here: same SASS.)
 constexpr int kDirectBatch = GRAND_DIRECT_BATCH;   // STAGE_DIRECT: neighbour rows in flight per warp (divided by R)
 
 // q.k over one head, then the reference's division by np.sqrt(d_k) (:196); for d_k a power of 4 the division is an
@@ -165,27 +125,6 @@ split_row_merge_kernel(GraphView g, int H, const float* __restrict__ split_stats
   }
 }
 
-// ---- epilogue operands of one row towards L1 while the row's neighbours are being gathered ------------------------------
-// A row's epilogue reads x_i, x0_i and the stage-combine terms (up to 6 x 512 B for rk4 on ogbn-arxiv).  Issued as plain
-// loads after the gather they cost one exposed round trip per row (ncu: ~25 % of the stall samples of the kernel sat on
-// those loads).  One prefetch instruction per lane -- lane -> (tensor, 128-byte line) -- starts all of them before the
-// gather loop at no register cost; the loads in finish_row then hit L1.  MEASURED SLOWER (see GRAND_EPI_PREFETCH): kept
-// as a build switch for the record, off by default.
-__device__ __forceinline__ void prefetch_row_operands(const RhsArgs& A, int row, int lane) {
-  const int row_bytes = A.d * (int)sizeof(float);
-  const int lines = (row_bytes + 127) >> 7;
-  const int n_tensors = 1 + (A.ep.x0 != nullptr ? 1 : 0) + (A.ep.y_out != nullptr ? A.ep.n_terms : 0);
-  const size_t off = (size_t)row * row_bytes;
-  for (int idx = lane; idx < n_tensors * lines; idx += kWarp) {
-    const int ts = idx / lines, ln = idx - ts * lines;
-    const float* basep;
-    if (ts == 0) basep = A.x;
-    else if (A.ep.x0 != nullptr && ts == 1) basep = A.ep.x0;
-    else basep = A.ep.term[ts - 1 - (A.ep.x0 != nullptr ? 1 : 0)];
-    prefetch_l1(reinterpret_cast<const char*>(basep) + off + (size_t)ln * 128);
-  }
-}
-
 // ---- epilogue: residual + RK stage combine for one finished row -----------------------------------------------------
 template <int VEC, int R>
 __device__ __forceinline__ void finish_row(const RhsArgs& A, int row, int lane, float alpha, float beta,
@@ -201,7 +140,7 @@ __device__ __forceinline__ void finish_row(const RhsArgs& A, int row, int lane, 
       const float4 xi = ldg4(A.x + base + c);
       float4 s0 = make_float4(0.f, 0.f, 0.f, 0.f);
       if (A.ep.x0 != nullptr) s0 = ld_stream4_hint(A.ep.x0 + base + c, pol_stream);
-      constexpr int kTB = GRAND_EPI_TERMS_BATCH;   // stage-combine terms per batch of loads (rk4 needs <= 4, dopri5 up to 7)
+      constexpr int kTB = 4;   // stage-combine terms per batch of loads (rk4 needs <= 4, dopri5 up to 7)
       // every element initialised: a conditionally-written array ends up in LOCAL memory (ncu: more local than global
       // load requests in this kernel before the change), zero-initialised it stays in 16 registers
       float4 tv[kTB];
@@ -230,30 +169,11 @@ __device__ __forceinline__ void finish_row(const RhsArgs& A, int row, int lane, 
             y.z = fmaf(ct, tv[t].z, y.z); y.w = fmaf(ct, tv[t].w, y.w);
           }
         }
-#if GRAND_EPI_TERMS_BATCH == 4
         for (int t = kTB; t < A.ep.n_terms; ++t) {
           const float ct = epi_coef(A.ep, t);
           const float4 v = ld_stream4_hint(A.ep.term[t] + base + c, pol_stream);
           y.x = fmaf(ct, v.x, y.x); y.y = fmaf(ct, v.y, y.y); y.z = fmaf(ct, v.z, y.z); y.w = fmaf(ct, v.w, y.w);
         }
-#else
-        for (int t0 = kTB; t0 < A.ep.n_terms; t0 += kTB) {      // further batches of kTB loads, same summation order
-          float4 tw[kTB];
-#pragma unroll
-          for (int u = 0; u < kTB; ++u) {
-            tw[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (t0 + u < A.ep.n_terms) tw[u] = ld_stream4_hint(A.ep.term[t0 + u] + base + c, pol_stream);
-          }
-#pragma unroll
-          for (int u = 0; u < kTB; ++u) {
-            if (t0 + u < A.ep.n_terms) {
-              const float ct = epi_coef(A.ep, t0 + u);
-              y.x = fmaf(ct, tw[u].x, y.x); y.y = fmaf(ct, tw[u].y, y.y);
-              y.z = fmaf(ct, tw[u].z, y.z); y.w = fmaf(ct, tw[u].w, y.w);
-            }
-          }
-        }
-#endif
         // y_out is the next stage's gather source: keep it cacheable
         *reinterpret_cast<float4*>(A.ep.y_out + base + c) = y;
       }
@@ -311,12 +231,8 @@ rhs_window_kernel(const __grid_constant__ RhsArgs A) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
-#if GRAND_PERSISTENT
-  for (int t = A.tile_begin + blockIdx.x * kRhsWarps + warp; t < A.tile_end; t += gridDim.x * kRhsWarps) {
-#else
   const int t = A.tile_begin + blockIdx.x * kRhsWarps + warp;
   if (t >= A.tile_end) return;
-#endif
   const int d = A.d;
   const int row_bytes = d * (int)sizeof(float);
 
@@ -361,7 +277,6 @@ rhs_window_kernel(const __grid_constant__ RhsArgs A) {
     }
   }
   // epilogue inputs of the window's rows: contiguous rows, pull them towards L2 now (one 128-byte line per lane)
-#if GRAND_WINDOW_L2_PREFETCH
   if (VEC == 4) {
     const int lines = (nrows * row_bytes + 127) >> 7;
     for (int ln = lane; ln < lines; ln += kWarp) {
@@ -370,30 +285,7 @@ rhs_window_kernel(const __grid_constant__ RhsArgs A) {
       for (int tt = 0; tt < A.ep.n_terms; ++tt) prefetch_l2(reinterpret_cast<const char*>(A.ep.term[tt]) + off);
     }
   }
-#endif
 
-#if GRAND_GATHER_FIRST
-  // neighbour rows of the first batch of the window's first row: in flight across the whole score phase
-  constexpr int kPre = (kDirectBatch / R) < 2 ? 2 : (kDirectBatch / R);
-  float4 pre[kPre][R];
-  int pre_n = 0, pre_lo = 0;
-  if (STAGE == STAGE_DIRECT && VEC == 4) {
-    const int rr0 = __shfl_sync(kFull, rec.y, 0);
-    pre_lo = split < 0 ? ((rr0 >> 20) & 0x3f) : 0;
-    const int pre_hi = split < 0 ? ((rr0 >> 26) & 0x3f) : cnt;
-    pre_n = pre_hi - pre_lo < kPre ? pre_hi - pre_lo : kPre;
-#pragma unroll
-    for (int u = 0; u < kPre; ++u) {
-      const int ju = __shfl_sync(kFull, j, (pre_lo + u) & 31);
-#pragma unroll
-      for (int r = 0; r < R; ++r) {
-        pre[u][r] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (u < pre_n && (lane + r * kWarp) * 4 < d)
-          pre[u][r] = ldg4_hint(A.x + (size_t)ju * d + (lane + r * kWarp) * 4, pol_keep);
-      }
-    }
-  }
-#endif
   // ---- level 2b: per-edge weight ab = head-mean attention (or the given weight) -------------------------------------
   float ab = 0.f;
   if (MODE == MODE_WEIGHT) {
@@ -445,7 +337,7 @@ rhs_window_kernel(const __grid_constant__ RhsArgs A) {
           }
           float m, l, e;
           if (split < 0) {
-            m = GRAND_SEG_MAX(s);
+            m = seg_max_redux(s, smask);
             e = valid ? expf(s - m) : 0.f;
             l = seg_sum(e, lane, lo, hi);
           } else {
@@ -462,7 +354,7 @@ rhs_window_kernel(const __grid_constant__ RhsArgs A) {
         if (valid) s = fused_score(A.a, qi + h * A.a.dk, kj + h * A.a.dk, vec4) * ew;
         float m, l, e;
         if (split < 0) {
-          m = GRAND_SEG_MAX(s);
+          m = seg_max_redux(s, smask);
           e = valid ? expf(s - m) : 0.f;
           l = seg_sum(e, lane, lo, hi);
         } else {
@@ -564,7 +456,7 @@ rhs_window_kernel(const __grid_constant__ RhsArgs A) {
       }
       finish_row<VEC, R>(A, row0 + r0, lane, alpha, beta, pol_stream, acc);
     }
-    GRAND_EXIT_WINDOW;
+    return;
   }
 
   for (int kr = 0; kr < nrows; ++kr) {
@@ -579,7 +471,6 @@ rhs_window_kernel(const __grid_constant__ RhsArgs A) {
     for (int r = 0; r < R; ++r)
 #pragma unroll
       for (int v = 0; v < VEC; ++v) acc[r][v] = 0.f;
-    if (GRAND_EPI_PREFETCH && split < 0) prefetch_row_operands(A, row0 + kr, lane);
 
     if (STAGE == STAGE_CPASYNC || STAGE == STAGE_BULK) {
       if (full) {
@@ -614,22 +505,6 @@ rhs_window_kernel(const __grid_constant__ RhsArgs A) {
       constexpr int U = (kDirectBatch / R) < 2 ? 2 : (kDirectBatch / R);
       const float* xl = A.x + (size_t)lane * VEC;
       int e = e_lo;
-#if GRAND_GATHER_FIRST
-      if (VEC == 4 && kr == 0 && pre_n > 0) {        // the rows requested before the score phase (pre_lo == e_lo)
-#pragma unroll
-        for (int u = 0; u < kPre; ++u) {
-          const float a = __shfl_sync(kFull, ab, (pre_lo + u) & 31);
-          if (u < pre_n) {
-#pragma unroll
-            for (int r = 0; r < R; ++r) {
-              acc[r][0] = fmaf(a, pre[u][r].x, acc[r][0]); acc[r][1 % VEC] = fmaf(a, pre[u][r].y, acc[r][1 % VEC]);
-              acc[r][2 % VEC] = fmaf(a, pre[u][r].z, acc[r][2 % VEC]); acc[r][3 % VEC] = fmaf(a, pre[u][r].w, acc[r][3 % VEC]);
-            }
-          }
-        }
-        e += pre_n;
-      }
-#endif
       while (e_hi - e >= U) { gather_batch<VEC, R, U>(xl, d, lane, full, j, ab, e, pol_keep, acc); e += U; }
       if (U >= 8 && e_hi - e >= 4) { gather_batch<VEC, R, 4>(xl, d, lane, full, j, ab, e, pol_keep, acc); e += 4; }
       if (U >= 4 && e_hi - e >= 2) { gather_batch<VEC, R, 2>(xl, d, lane, full, j, ab, e, pol_keep, acc); e += 2; }
@@ -659,7 +534,7 @@ rhs_window_kernel(const __grid_constant__ RhsArgs A) {
     int old = 0;
     if (lane == 0) old = atomicAdd(A.split_counter + split, 1);
     old = __shfl_sync(kFull, old, 0);
-    if (old != slot1 - slot0 - 1) GRAND_EXIT_ROWLOOP;
+    if (old != slot1 - slot0 - 1) return;
     __threadfence();
 #pragma unroll
     for (int r = 0; r < R; ++r)
@@ -710,9 +585,6 @@ rhs_window_kernel(const __grid_constant__ RhsArgs A) {
     if (lane == 0) A.split_counter[split] = 0;   // leave the counter ready for the next launch
     finish_row<VEC, R>(A, row0, lane, alpha, beta, pol_stream, acc);
   }
-#if GRAND_PERSISTENT
-  }
-#endif
 }
 
 // ---- launchers ------------------------------------------------------------------------------------------------------------
@@ -736,12 +608,6 @@ template <int MODE, int VEC, int R, int STAGE>
 static int launch_rhs_inst(const RhsArgs& A, cudaStream_t stream) {
   int grid = (A.tile_end - A.tile_begin + kRhsWarps - 1) / kRhsWarps;
   if (grid <= 0) return GRAND_OK;
-#if GRAND_PERSISTENT
-  if (STAGE == STAGE_DIRECT || STAGE == STAGE_ROWBUF) {   // the shared-memory stagings keep one window per warp
-    const int cap = num_sms() * GRAND_DIRECT_MINBLOCKS * GRAND_PERSISTENT;
-    if (grid > cap) grid = cap;
-  }
-#endif
   size_t smem = 0;
   if (STAGE == STAGE_CPASYNC || STAGE == STAGE_BULK) smem = (size_t)kRhsWarps * ((size_t)GRAND_TILE * A.d * sizeof(float) + 16);
   if (STAGE == STAGE_ROWBUF) smem = (size_t)kRhsWarps * GRAND_MAX_PACKED_ROWS * A.d * sizeof(float);

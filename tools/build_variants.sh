@@ -4,7 +4,7 @@
 # shipped to the GPU box by gpurun).  Time them in one process with tools/edge_ab.py, or select one at run time with
 # GRAND_LIB=/root/repo/graph-neural-pde_b200/build/variants/lib_<name>.so.
 #   tools/build_variants.sh t448:-DGRAND_STREAM_THREADS=448 "t384b4:-DGRAND_STREAM_THREADS=384 -DGRAND_STREAM_BATCH=4"
-#   SRC=rhs_window.cu tools/build_variants.sh shfl:-DGRAND_SEGMAX_SHUFFLE=1
+#   SRC=rhs_ring.cu tools/build_variants.sh ring12:-DGRAND_RING_WARPS=12
 set -e
 cd "$(dirname "$0")/../graph-neural-pde_b200"
 SRC=${SRC:-rhs_stream.cu}
