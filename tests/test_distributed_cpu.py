@@ -130,3 +130,40 @@ def test_sharded_rhs_equals_global_rhs_gloo(world):
     assert p.exitcode == 0
   for rank, err in results:
     assert err < 2e-6, 'rank %d: %.3e' % (rank, err)
+
+
+def test_locality_order_shrinks_the_halo_on_a_graph_with_communities():
+  """distributed.locality_order (label propagation) + relabel: on a planted-partition graph whose node ids were
+  shuffled, the contiguous shards of `Partition` cut most edges in id order and few after the renumbering; on the
+  community-free Chung-Lu graph of the bench there is nothing to find.  The renumbered problem is the same problem:
+  the oracle's RHS commutes with the permutation."""
+  import numpy as np
+  from graph_neural_pde_b200.distributed import Partition, locality_order, relabel
+  from oracle import grand_oracle as O
+  rng = np.random.default_rng(0)
+  n, k = 4000, 8
+  comm = rng.integers(0, k, n)                                  # shuffled ids: community membership is random in id order
+  src = rng.integers(0, n, 60000)
+  same = rng.random(60000) < 0.995                              # 99.5 % of the edges stay inside a community
+  members = [np.nonzero(comm == c)[0] for c in range(k)]
+  dst = np.where(same, np.array([members[comm[s]][rng.integers(0, len(members[comm[s]]))] for s in src]),
+                 rng.integers(0, n, 60000))
+  ei = torch.from_numpy(np.stack([np.concatenate([src, dst, np.arange(n)]), np.concatenate([dst, src, np.arange(n)])]))
+  perm, inv = locality_order(ei, n)
+  assert sorted(perm.tolist()) == list(range(n)) and torch.equal(inv[perm], torch.arange(n))
+  ei2 = relabel(ei, inv)
+  for world in (2, 4, 8):
+    before = max(Partition(ei, n, world, r).summary()['halo_fraction_of_graph'] for r in range(world))
+    after = max(Partition(ei2, n, world, r).summary()['halo_fraction_of_graph'] for r in range(world))
+    assert after < 0.5 * before, (world, before, after)
+  # same problem: f(x)[perm] == f'(x[perm]) with the relabelled edge list (edge order preserved)
+  torch.manual_seed(0)
+  d, ad, h = 8, 8, 2
+  x = torch.randn(n, d, dtype=torch.float64)
+  opt = default_opt(hidden_dim=d, attention_dim=ad, heads=h)
+  P = {'Q.weight': torch.randn(ad, d, dtype=torch.float64), 'Q.bias': torch.randn(ad, dtype=torch.float64),
+       'K.weight': torch.randn(ad, d, dtype=torch.float64), 'K.bias': torch.randn(ad, dtype=torch.float64)}
+  a, b = torch.tensor(0.3, dtype=torch.float64), torch.tensor(0.1, dtype=torch.float64)
+  f = O.transformer_rhs(x, ei, P, opt, a, b, x)
+  f2 = O.transformer_rhs(x[perm], ei2, P, opt, a, b, x[perm])
+  assert float((f[perm] - f2).abs().max()) < 1e-12
