@@ -79,11 +79,24 @@ class ODEFunc(nn.Module):
     self._engine = None
 
   def engine(self, x):
-    """The CUDA engine for the current graph and state width (built on first use)."""
+    """The CUDA engine for the current graph and state width (built on first use).  The engines of the last TWO edge
+    lists are kept: the hard-attention block alternates between the full graph (evaluation) and a freshly sampled one
+    (every training forward, reference src/block_transformer_hard_attention.py:49-68), and the full graph's plan should not
+    be rebuilt after every training step.  An entry is only reused for the very tensor object it was built from (the
+    entry holds a reference to it, so its identity cannot be recycled)."""
     d = int(x.shape[1])
     if self._engine is None or self._engine.d != d or self._engine.device != x.device:
-      plan = GraphPlan(self._edge_index, num_nodes=x.shape[0], device=x.device)
-      self._engine = RhsEngine(plan, d)
+      cache = self.__dict__.setdefault('_engine_cache', [])
+      for i, (ei, eng) in enumerate(cache):
+        if ei is self._edge_index and eng.d == d and eng.device == x.device:
+          cache.append(cache.pop(i))                      # most recently used last
+          self._engine = eng
+          break
+      else:
+        plan = GraphPlan(self._edge_index, num_nodes=x.shape[0], device=x.device)
+        self._engine = RhsEngine(plan, d)
+        cache.append((self._edge_index, self._engine))
+        del cache[:-2]
     return self._engine
 
   def _bump_nfe(self, count=1):

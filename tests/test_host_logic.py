@@ -429,3 +429,40 @@ def test_native_plan_rejects_bad_edge_lists():
     GraphPlan(torch.tensor([[0, 5], [1, 1]]), 3, device='cpu')
   with pytest.raises(AssertionError, match='out of range'):
     GraphPlan(torch.tensor([[0, 1], [1, -1]]), 3, device='cpu')
+
+
+def test_function_keeps_the_engines_of_the_last_two_edge_lists(monkeypatch):
+  """ODEFunc.engine: reassigning `edge_index` drops the current engine (reference src/run_GNN.py:252-254 reassigns it),
+  but going back to a recently used edge-list OBJECT (hard attention: full graph in evaluation, a new sample every
+  training forward) reuses its engine instead of rebuilding the plan."""
+  from graph_neural_pde_b200 import base_classes as BC
+  built = []
+
+  class FakePlan:
+    def __init__(self, ei, num_nodes, device):
+      built.append(ei)
+
+  class FakeEngine:
+    def __init__(self, plan, d):
+      self.d, self.device = d, torch.device('cpu')
+
+  monkeypatch.setattr(BC, 'GraphPlan', FakePlan)
+  monkeypatch.setattr(BC, 'RhsEngine', FakeEngine)
+  f = BC.ODEFunc(default_opt(), Data(x=torch.zeros(4, 8), edge_index=torch.zeros(2, 0, dtype=torch.long), edge_attr=None,
+                                     num_nodes=4), torch.device('cpu'))
+  x = torch.zeros(4, 8)
+  full = torch.tensor([[0, 1], [1, 0]])
+  f.edge_index = full
+  e_full = f.engine(x)
+  assert f.engine(x) is e_full and len(built) == 1
+  for k in range(3):                                   # train forward (new sample), then evaluation (full graph)
+    sample = torch.tensor([[0], [1]])
+    f.edge_index = sample
+    e_s = f.engine(x)
+    assert e_s is not e_full and len(built) == 2 + k
+    f.edge_index = full
+    assert f.engine(x) is e_full and len(built) == 2 + k     # no rebuild of the full graph's plan
+  other = torch.tensor([[0, 1], [1, 0]])               # equal content, different object: a new plan, as before
+  f.edge_index = other
+  assert f.engine(x) is not e_full and len(built) == 5
+  assert f.engine(torch.zeros(4, 12)) is not f.engine(x)      # another state width: another engine
